@@ -1,0 +1,284 @@
+"""TEST INFRASTRUCTURE ONLY -- generates tests/golden/*.pt by executing the UNMODIFIED reference
+(/root/reference, imported through oracle/ref_shim.py) on CPU fp32, and cross-checks the oracle
+restatement against it while doing so.  Run in the build container (the reference does not exist
+on the GPU box):
+
+    python oracle/make_golden.py            # writes tests/golden/*.pt, prints oracle-vs-reference errors
+
+Fixtures hold inputs' seeds + reference OUTPUTS only; weights are regenerated from seeds by
+oracle.unet_oracle.make_weights (bit-identical on any host with the same torch build).
+"""
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import ref_shim                                   # noqa: E402
+from oracle import unet_oracle as UO                          # noqa: E402
+from oracle import vae_oracle as VO                           # noqa: E402
+from oracle import samplers_oracle as SO                      # noqa: E402
+
+GOLD = os.path.join(ROOT, 'tests', 'golden')
+
+
+def build_ref_unet(m, cfg: UO.UNetConfig):
+    return m.UNetSD(in_dim=cfg.in_dim, dim=cfg.dim, y_dim=768, context_dim=cfg.context_dim,
+                    out_dim=cfg.out_dim, dim_mult=list(cfg.dim_mult), num_heads=cfg.num_heads,
+                    head_dim=cfg.head_dim, num_res_blocks=cfg.num_res_blocks,
+                    attn_scales=list(cfg.attn_scales), dropout=0.1, temporal_attention=True).eval()
+
+
+def synth_inputs(F, h, w, L=77, ctx_dim=1024, seed=123):
+    """x_T exactly as samplers_common.py:118-119 (CPU generator seeded per run); cond/uncond from seed 2."""
+    g = torch.Generator('cpu').manual_seed(seed)
+    x = torch.randn((1, 4, F, h, w), generator=g)
+    g2 = torch.Generator('cpu').manual_seed(2)
+    c = torch.randn(1, L, ctx_dim, generator=g2)
+    uc = torch.randn(1, L, ctx_dim, generator=g2)
+    return x, c, uc
+
+
+def gold_unet(m, name, cfg, F, h, w, wseed, keep_taps):
+    torch.manual_seed(0)
+    net = build_ref_unet(m, cfg)
+    specs = UO.param_specs(cfg)
+    sd = net.state_dict()
+    assert set(sd) == set(specs), (set(sd) ^ set(specs))
+    for k in sd:
+        assert tuple(sd[k].shape) == specs[k], k
+    W = UO.make_weights(specs, seed=wseed)
+    net.load_state_dict(W, strict=True)
+    x, c, uc = synth_inputs(F, h, w, ctx_dim=cfg.context_dim)
+    t = torch.tensor([981])
+    ref_taps = {}
+    hooks = []
+    if keep_taps:
+        for mname, mod in net.named_modules():
+            if mname in keep_taps:
+                hooks.append(mod.register_forward_hook(
+                    lambda mod_, inp, out, n=mname: ref_taps.__setitem__(n, out.detach().clone())))
+    t0 = time.time()
+    with torch.no_grad():
+        eps_c = net(x, t, c)
+        for hk in hooks:
+            hk.remove()
+        eps_u = net(x, t, uc)
+    dt = time.time() - t0
+    taps = {}
+    o_c = UO.unet_forward(W, cfg, x, t, c, taps)
+    o_u = UO.unet_forward(W, cfg, x, t, uc)
+    err = max((o_c - eps_c).abs().max().item(), (o_u - eps_u).abs().max().item())
+    print(f'[{name}] reference 2 forwards {dt:.1f}s; oracle-vs-reference max|d| = {err:.3e} '
+          f'(ref absmax {eps_c.abs().max().item():.3f})')
+    assert err < 2e-4
+    out = {'cfg': cfg.__dict__, 'F': F, 'h': h, 'w': w, 'wseed': wseed, 'x_seed': 123, 'ctx_seed': 2,
+           't': 981, 'eps_cond': eps_c, 'eps_uncond': eps_u}
+    for n, v in ref_taps.items():
+        # 5-D temporal modules are hooked in b c f h w; store everything as (b f) c h w
+        if v.dim() == 5:
+            v = v.permute(0, 2, 1, 3, 4).reshape(-1, v.shape[1], v.shape[3], v.shape[4])
+        d = (taps[n] - v).abs().max().item()
+        assert d < 2e-4, (n, d)
+        out['tap:' + n] = v.half()
+    # one sampler step of each scheduler from x_T, produced by the reference sampler classes: the
+    # denoiser is wrapped so that the latent handed to the (n+1)-th model call -- i.e. the state after
+    # the first update -- is captured and the run is then aborted.
+    smp = ref_shim.load_samplers()
+    betas = SO.linear_sd_betas()
+    net.register_schedule(given_betas=betas.numpy())
+    smp.SamplerBase('x', None).register_buffers_to_model(net, betas, torch.device('cpu'))
+    from samplers.ddim.gaussian_sampler import GaussianDiffusion
+    from samplers.ddim.sampler import DDIMSampler
+    from samplers.uni_pc.sampler import UniPCSampler
+    import samplers.uni_pc.sampler as ups
+    ups.UniPCSampler.register_buffer = lambda self, nm, attr: setattr(self, nm, attr)   # see gold_samplers
+
+    class _Stop(Exception):
+        pass
+
+    class Wrapped:
+        def __init__(self, stop_at):
+            self.calls, self.stop_at = [], stop_at
+            for a_ in ('device', 'betas', 'alphas_cumprod', 'alphas_cumprod_prev', 'num_timesteps',
+                       'parameterization'):
+                setattr(self, a_, getattr(net, a_))
+
+        def __call__(self, xx, tt, cc):
+            self.calls.append(xx.clone())
+            if len(self.calls) == self.stop_at:
+                raise _Stop()
+            return net(xx, tt, cc)
+
+    def first_update(run, stop_at):
+        wm = Wrapped(stop_at)
+        try:
+            run(wm)
+        except _Stop:
+            pass
+        return wm.calls[-1]
+
+    S = 50
+    out['ddim_gaussian_x1'] = first_update(
+        lambda wm: GaussianDiffusion(wm, betas).sample(x_T=x, S=S, conditioning=c, unconditional_conditioning=uc,
+                                                       unconditional_guidance_scale=17.0, eta=0.0), 3)
+    out['ddim_x1'] = first_update(
+        lambda wm: DDIMSampler(wm, device=torch.device('cpu')).sample(
+            S=S, batch_size=1, shape=tuple(x.shape), conditioning=c, x_T=x, unconditional_guidance_scale=17.0,
+            unconditional_conditioning=uc, eta=0.0), 3)
+    out['unipc_x1'] = first_update(
+        lambda wm: UniPCSampler(wm).sample(S=30, batch_size=1, shape=tuple(x.shape), conditioning=c, x_T=x,
+                                           unconditional_guidance_scale=17.0, unconditional_conditioning=uc,
+                                           strength=None), 5)
+    # the oracle samplers driven by the oracle UNet must hand the same latent to the same model call
+    # (for UniPC the 5th call receives the *predictor* output of the 2nd update, uni_pc.py:630-645)
+    class OWrapped:
+        def __init__(self, stop_at):
+            self.calls, self.stop_at = [], stop_at
+
+        def __call__(self, xx, tt, cc):
+            self.calls.append(xx.clone())
+            if len(self.calls) == self.stop_at:
+                raise _Stop()
+            return UO.unet_forward(W, cfg, xx, tt, cc)
+
+    for key, stop_at, fn in (
+            ('ddim_gaussian_x1', 3, lambda om: SO.ddim_gaussian_sample(om, betas, x, S, c, uc, 17.0)),
+            ('ddim_x1', 3, lambda om: SO.ddim_sample(om, betas, x, S, c, uc, 17.0)),
+            ('unipc_x1', 5, lambda om: SO.unipc_sample(om, betas, x, 30, c, uc, 17.0))):
+        om = OWrapped(stop_at)
+        try:
+            fn(om)
+        except _Stop:
+            pass
+        d = (om.calls[-1] - out[key]).abs().max().item()
+        print(f'[{name}] {key}: oracle-vs-reference max|d| = {d:.3e}')
+        assert d < 5e-4, (key, d)
+    torch.save(out, os.path.join(GOLD, name + '.pt'))
+    return out
+
+
+class _SchedModel:
+    """Stand-in denoiser exposing what the reference samplers read from the model
+    (ddim/sampler.py:14,27-33; uni_pc/sampler.py:11-12; samplers_common.py:77-83)."""
+
+    def __init__(self, betas):
+        self.device = torch.device('cpu')
+        self.betas = betas
+        self.alphas_cumprod = torch.cumprod(1 - betas, dim=0)
+        acp = self.alphas_cumprod.numpy()
+        self.alphas_cumprod_prev = torch.tensor(np.append(1.0, acp[:-1]), dtype=torch.float32)
+        self.num_timesteps = len(betas)
+        self.parameterization = 'eps'
+
+    def __call__(self, x, t, c):
+        return analytic_model(x, t, c)
+
+
+def analytic_model(x, t, c):
+    """Cheap deterministic eps-model used to pin the schedulers without a UNet."""
+    tt = t.float().view(-1, *((1,) * (x.ndim - 1))) / 1000.0
+    bias = c.float().mean() if c is not None else 0.0
+    ch = torch.arange(x.shape[1], dtype=x.dtype).view(1, -1, *((1,) * (x.ndim - 2)))
+    return (torch.tanh(0.8 * x + 0.5 * tt + 0.1 * ch) * 0.9 + 0.3 * bias + 0.05 * torch.roll(x, 1, dims=2)).to(x.dtype)
+
+
+def gold_samplers():
+    ref_shim.load_samplers()
+    from samplers.ddim.gaussian_sampler import GaussianDiffusion
+    from samplers.ddim.sampler import DDIMSampler
+    from samplers.uni_pc.sampler import UniPCSampler
+    import samplers.uni_pc.sampler as ups
+    betas = SO.linear_sd_betas()
+    g = torch.Generator('cpu').manual_seed(123)
+    x = torch.randn((1, 4, 5, 6, 7), generator=g)
+    c = torch.full((1, 77, 8), 0.25)
+    uc = torch.full((1, 77, 8), -0.5)
+    model = _SchedModel(betas)
+    out = {'x_seed': 123, 'shape': tuple(x.shape), 'c_val': 0.25, 'uc_val': -0.5}
+    for S, scale in ((50, 17.0), (20, 7.5), (7, 1.0)):
+        torch.manual_seed(7)
+        r = GaussianDiffusion(model, betas).sample(x_T=x, S=S, conditioning=c, unconditional_conditioning=uc,
+                                                   unconditional_guidance_scale=scale, eta=0.0)
+        torch.manual_seed(7)
+        o = SO.ddim_gaussian_sample(model, betas, x, S, c, uc, scale)
+        print(f'[samplers] DDIM_Gaussian S={S} g={scale}: oracle-vs-reference max|d| = {(r - o).abs().max().item():.3e}')
+        assert torch.allclose(r, o, rtol=0, atol=1e-6)
+        out[f'ddim_gaussian_S{S}_g{scale}'] = r
+        torch.manual_seed(7)
+        r = DDIMSampler(model, device=torch.device('cpu')).sample(
+            S=S, batch_size=1, shape=tuple(x.shape), conditioning=c, x_T=x,
+            unconditional_guidance_scale=scale, unconditional_conditioning=uc, eta=0.0)
+        torch.manual_seed(7)
+        o = SO.ddim_sample(model, betas, x, S, c, uc, scale)
+        print(f'[samplers] DDIM S={S} g={scale}: oracle-vs-reference max|d| = {(r - o).abs().max().item():.3e}')
+        assert torch.allclose(r, o, rtol=0, atol=1e-6)
+        out[f'ddim_S{S}_g{scale}'] = r
+    # UniPCSampler.register_buffer hard-codes torch.device("cuda") (uni_pc/sampler.py:14-18): keep it on CPU here
+    ups.UniPCSampler.register_buffer = lambda self, name, attr: setattr(self, name, attr)
+    for S, scale in ((30, 17.0), (12, 7.5), (5, 1.0)):
+        r = UniPCSampler(model).sample(S=S, batch_size=1, shape=tuple(x.shape), conditioning=c, x_T=x,
+                                       unconditional_guidance_scale=scale, unconditional_conditioning=uc,
+                                       strength=None)
+        o = SO.unipc_sample(model, betas, x, S, c, uc, scale)
+        print(f'[samplers] UniPC S={S} g={scale}: oracle-vs-reference max|d| = {(r - o).abs().max().item():.3e}')
+        assert torch.allclose(r, o, rtol=0, atol=2e-5)
+        out[f'unipc_S{S}_g{scale}'] = r
+    # with eta > 0 (consumes the global RNG identically)
+    torch.manual_seed(11)
+    r = DDIMSampler(model, device=torch.device('cpu')).sample(
+        S=10, batch_size=1, shape=tuple(x.shape), conditioning=c, x_T=x,
+        unconditional_guidance_scale=3.0, unconditional_conditioning=uc, eta=0.5)
+    torch.manual_seed(11)
+    o = SO.ddim_sample(model, betas, x, 10, c, uc, 3.0, eta=0.5)
+    assert torch.allclose(r, o, rtol=0, atol=1e-6)
+    out['ddim_S10_g3.0_eta0.5_seed11'] = r
+    torch.save(out, os.path.join(GOLD, 'samplers.pt'))
+
+
+def gold_vae(m):
+    cfg = VO.VAEConfig()
+    ddconfig = {'double_z': True, 'z_channels': 4, 'resolution': 256, 'in_channels': 3, 'out_ch': 3, 'ch': 128,
+                'ch_mult': [1, 2, 4, 4], 'num_res_blocks': 2, 'attn_resolutions': [], 'dropout': 0.0}
+    torch.manual_seed(0)
+    ae = m.AutoencoderKL(ddconfig, 4, None).eval()
+    specs = VO.decoder_param_specs(cfg)
+    sd = ae.state_dict()
+    dec_keys = {k for k in sd if k.startswith('decoder.') or k.startswith('post_quant_conv.')}
+    assert dec_keys == set(specs), dec_keys ^ set(specs)
+    for k in specs:
+        assert tuple(sd[k].shape) == specs[k], k
+    W = UO.make_weights(specs, seed=3)
+    sd.update(W)
+    ae.load_state_dict(sd, strict=True)
+    g = torch.Generator('cpu').manual_seed(5)
+    z = torch.randn((2, 4, 8, 16), generator=g) / 0.18215 * 0.8
+    with torch.no_grad():
+        ref = ae.decode(z)
+    o = VO.vae_decode(W, cfg, z)
+    err = (o - ref).abs().max().item()
+    print(f'[vae] oracle-vs-reference max|d| = {err:.3e} (ref absmax {ref.abs().max().item():.3f})')
+    assert err < 1e-3 * max(1.0, ref.abs().max().item())
+    torch.save({'wseed': 3, 'z_seed': 5, 'z_shape': (2, 4, 8, 16), 'z_scale': 0.8 / 0.18215, 'out': ref},
+               os.path.join(GOLD, 'vae_decode.pt'))
+
+
+def main():
+    os.makedirs(GOLD, exist_ok=True)
+    m = ref_shim.load_modelscope()
+    gold_samplers()
+    gold_vae(m)
+    tiny = UO.UNetConfig(dim=64)
+    keep = ['input_blocks.0.0', 'input_blocks.0.1', 'input_blocks.1.0', 'input_blocks.1.1', 'input_blocks.1.2',
+            'input_blocks.3', 'input_blocks.4.0', 'input_blocks.11.0', 'middle_block.1', 'middle_block.3',
+            'output_blocks.0.0', 'output_blocks.2.1', 'output_blocks.5.3', 'output_blocks.11.2']
+    gold_unet(m, 'unet_tiny', tiny, F=3, h=16, w=8, wseed=1, keep_taps=keep)
+    if os.environ.get('T2V_GOLD_FULL', '1') == '1':
+        gold_unet(m, 'unet_cfg1', UO.UNetConfig(), F=4, h=16, w=16, wseed=0, keep_taps=[])
+
+
+if __name__ == '__main__':
+    main()
