@@ -1,0 +1,136 @@
+/* t2v_b200 -- C ABI of the B200-native text2video denoising path.
+ *
+ * The reference (kabachuha/sd-webui-text2video) has NO FFI boundary: its hot path is plain Python that calls
+ * PyTorch library kernels.  This header is the boundary a maintainer would bind instead (ctypes stubs in
+ * INTEGRATION.md); every entry point names the reference call it replaces (paths relative to
+ * /root/reference/scripts).
+ *
+ * Conventions (mirroring the Python contract):
+ *   - plain pointers and sizes only; device pointers unless stated otherwise; the CALLER owns every tensor passed
+ *     in, the library owns only its packed-weight and workspace arenas (freed by *_destroy)
+ *   - all work is enqueued asynchronously on `stream` (a cudaStream_t passed as void*), no hidden synchronisation
+ *   - return value 0 = success, negative = error (t2v_last_error() gives the text); the Python layer raises
+ *     RuntimeError so failures surface as exceptions exactly like the reference (t2v_helpers/render.py:35-37)
+ *   - a handle is bound to one device and is not thread-safe (the webui serialises callers, text2vid.py:82)
+ */
+#ifndef T2V_B200_H
+#define T2V_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------------------------------ library */
+int t2v_init(int device);                 /* selects the device, resolves driver entry points, sizes grids */
+const char* t2v_last_error(void);
+int t2v_num_sms(void);
+const char* t2v_version(void);
+
+/* ------------------------------------------------------------------------------------------ denoiser
+ * replaces modelscope/t2v_model.py::UNetSD (ctor :98-326, forward :386-501).                            */
+typedef struct t2v_unet t2v_unet;
+
+typedef struct {
+    int in_dim, dim, context_dim, out_dim;
+    int dim_mult[8];
+    int n_mult;
+    int num_heads;        /* heads of the stem TemporalTransformer (:171-179) */
+    int head_dim;         /* must be 64 */
+    int num_res_blocks;
+    float attn_scales[8];
+    int n_attn_scales;
+} t2v_unet_config;
+
+int t2v_unet_create(const t2v_unet_config* cfg, t2v_unet** out);
+void t2v_unet_destroy(t2v_unet* u);
+/* Hands one parameter of the reference state_dict (key names of SURVEY.md appendix D, e.g.
+ * "input_blocks.1.0.in_layers.2.weight") to the library, which packs it into its own layout.
+ * `data` is a DEVICE pointer to a contiguous tensor of `dtype` (0 = fp16, 1 = fp32) with `ndim` dims.
+ * Replaces load_state_dict(strict=True) at modelscope/t2v_pipeline.py:95-101 (and is what the LoRA merger's
+ * re-assigned .weight tensors are re-sent through, stable_lora/scripts/lora_processor.py:236-242).        */
+int t2v_unet_set_param(t2v_unet* u, const char* name, const void* data, int dtype, int ndim, const int64_t* shape,
+                       void* stream);
+/* Number of parameters still missing (0 => ready); fills `name_out` with one missing key if non-null. */
+int t2v_unet_missing_params(t2v_unet* u, char* name_out, size_t name_cap);
+/* eps = UNetSD.forward(x, t, y) (t2v_model.py:386-459).
+ *   x   [B, in_dim, F, h, w]  fp32 (x_is_f32 = 1) or fp16, NCFHW exactly as the samplers hold the latent
+ *   t   [B] float32 (host converts int64 timesteps; UniPC already passes floats, uni_pc.py:248)
+ *   ctx [B, L, context_dim] fp16
+ *   out [B, out_dim, F, h, w] fp16 (out_is_f32 = 0) or fp32                                               */
+int t2v_unet_forward(t2v_unet* u, const void* x, int x_is_f32, const float* t, const void* ctx, void* out,
+                     int out_is_f32, int B, int F, int h, int w, int L, void* stream);
+/* 2*MAC flop count of one forward at this shape (for roofline reporting). */
+double t2v_unet_flops(t2v_unet* u, int B, int F, int h, int w, int L);
+int t2v_unet_num_launches(t2v_unet* u);
+/* copies an internal activation (debug / parity taps): name = reference module path (e.g. "input_blocks.1.0"),
+ * dst receives [(B F), C, h, w] fp16 as the reference module returns it. Returns element count or <0. */
+long long t2v_unet_read_tap(t2v_unet* u, const char* name, void* dst, long long cap_elems, void* stream);
+int t2v_unet_enable_taps(t2v_unet* u, int on);
+
+/* ------------------------------------------------------------------------------------------ VAE decoder
+ * replaces AutoencoderKL.decode (modelscope/t2v_model.py:1646-1649) + ldm Decoder (vendored twin
+ * videocrafter/lvdm/models/modules/autoencoder_modules.py:484-596) and the per-frame loop of
+ * t2v_pipeline.py:329-355 (all frames batched).                                                           */
+typedef struct t2v_vae t2v_vae;
+typedef struct {
+    int ch;
+    int ch_mult[8];
+    int n_mult;
+    int num_res_blocks;
+    int z_channels;
+    int out_ch;
+    int embed_dim;
+} t2v_vae_config;
+int t2v_vae_create(const t2v_vae_config* cfg, t2v_vae** out);
+void t2v_vae_destroy(t2v_vae* v);
+int t2v_vae_set_param(t2v_vae* v, const char* name, const void* data, int dtype, int ndim, const int64_t* shape,
+                      void* stream);
+int t2v_vae_missing_params(t2v_vae* v, char* name_out, size_t name_cap);
+/* z [B, z_channels, F, h, w] fp32/fp16 latent as returned by the sampler; multiplied by `z_scale`
+ * (1/0.18215, t2v_pipeline.py:348) on ingest.
+ *   out_mode 0: float32 [B*F, 3, 8h, 8w] in [-1, 1]   (what AutoencoderKL.decode returns, per frame)
+ *   out_mode 1: uint8   [B*F, 8h, 8w, 3] RGB, tensor2vid arithmetic (t2v_pipeline.py:447-460)          */
+int t2v_vae_decode(t2v_vae* v, const void* z, int z_is_f32, float z_scale, void* out, int out_mode, int B, int F, int h,
+                   int w, void* stream);
+double t2v_vae_flops(t2v_vae* v, int nframes, int h, int w);
+
+/* ------------------------------------------------------------------------------------------ sampler steps
+ * replace the per-step tensor arithmetic of scripts/samplers (ddim/gaussian_sampler.py:125-136,:269-283;
+ * ddim/sampler.py:176-218; uni_pc/uni_pc.py:299-307,:378-391,:625-650).                                  */
+int t2v_ddim_step(const float* x, const void* eps_c, const void* eps_u, float* x_out, long long n, long long chan_stride,
+                  int C, int guided_channels, float g, int mode, float a0, float a1, float a2, float a3, float a4,
+                  const float* noise, int cfg_fp16, void* stream);
+int t2v_cfg_x0(const float* x, const void* eps_c, const void* eps_u, float* x0, long long n, float g, float alpha,
+               float sigma, int cfg_fp16, void* stream);
+int t2v_lincomb(float* out, const float* const* src, const float* coef, int n_src, long long n, void* stream);
+
+/* ------------------------------------------------------------------------------------------ kernel-level entry
+ * points (used by the parity tests; the model-level calls above are built from exactly these launchers).   */
+int t2v_op_gemm(const void* a, long long lda, int K, int nd, const int* dims, int ntaps, const int* tap_off,
+                const void* w_packed, int n_alloc, int N, int b_batch_dim, int flags, void* out, long long ldo,
+                const void* bias, int bias_rows, long long bias_stride, const void* residual, long long ldr,
+                float alpha, int force_bn, void* stream);
+int t2v_op_pack_conv_weight(const void* src, int src_is_f32, void* dst, int Cout, int Cin, int taps, int n_alloc,
+                            int k_alloc, void* stream);
+int t2v_op_pack_geglu_weight(const void* w, const void* b, int src_is_f32, void* wdst, void* bdst, int H, int K, int bn,
+                             void* stream);
+int t2v_op_groupnorm(const void* x, long long ldx, void* y, long long ldy, long long rows, int C, int rows_per_inst,
+                     const void* gamma, const void* beta, float eps, int silu, void* stream);
+int t2v_op_layernorm(const void* x, long long ldx, void* y, long long ldy, long long rows, int C, const void* gamma,
+                     const void* beta, float eps, void* stream);
+int t2v_op_attention(const void* q, const void* k, const void* v, void* o, long long q_bs, long long q_ss,
+                     long long k_bs, long long k_ss, long long v_bs, long long v_ss, long long o_bs, long long o_ss,
+                     int batch, int heads, int sq, int skv, int kv_batch_div, float scale, void* stream);
+int t2v_op_upsample2x(const void* x, void* y, int nframes, int h, int w, int C, void* stream);
+int t2v_op_im2col_s2(const void* x, void* col, int nframes, int h, int w, int C, void* stream);
+int t2v_op_time_sinusoid(const float* t, void* out, int B, int dim, void* stream);
+int t2v_op_small_linear(const void* x, long long ldx, const void* W, const void* bias, const void* addend, void* y,
+                        long long ldy, int B, int N, int K, int silu_in, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* T2V_B200_H */

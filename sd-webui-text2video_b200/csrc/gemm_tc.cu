@@ -1,0 +1,481 @@
+// tcgen05 / TMEM / TMA implicit-GEMM kernel (sm_100a).  See gemm_tc.cuh for the data model.
+//
+// Per CTA (persistent, 192 threads, 1 CTA/SM):
+//   warp 0      TMA producer  : per k-iteration one A box (128 rows x 64 K, tap-shifted coordinates, OOB = zero
+//                               padding) + one B box (BN x 64 K) into a SWIZZLE_128B smem ring
+//   warp 1      MMA issuer    : lane 0 issues 4 x tcgen05.mma (M=128, N=BN, K=16) per stage into a double-buffered
+//                               fp32 accumulator in TMEM; tcgen05.commit releases the smem stage / publishes the tile
+//   warps 2..5  epilogue      : tcgen05.ld 32 lanes x 32 columns -> registers -> alpha, bias, residual, GEGLU -> HBM
+// Roofline: tensor-bound (2*M*N*K*taps flop per launch) whenever K*taps is large; see DESIGN.md.
+#include "gemm_tc.cuh"
+#include "ptx.cuh"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+
+namespace t2v {
+
+namespace {
+
+constexpr int kThreads = 192;
+constexpr int kABytes = GEMM_BLOCK_M * GEMM_BLOCK_K * 2;   // 16 KB
+constexpr int kSmemBudget = 200 * 1024;                     // ring budget (barriers + alignment slack on top)
+
+template <int BN>
+struct Cfg {
+    static constexpr int kBBytes = BN * GEMM_BLOCK_K * 2;
+    static constexpr int kStageBytes = kABytes + kBBytes;
+    static constexpr int kStages = (kSmemBudget / kStageBytes) > 8 ? 8 : (kSmemBudget / kStageBytes);
+    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_constant__ GemmDesc g) {
+    using C = Cfg<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);      // SWIZZLE_128B atoms need 1024 B alignment
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes);
+    uint64_t* full = bars;                       // [kStages] TMA -> MMA
+    uint64_t* empty = bars + C::kStages;         // [kStages] MMA -> TMA
+    uint64_t* tfull = bars + 2 * C::kStages;     // [2] MMA -> epilogue
+    uint64_t* tempty = tfull + 2;                // [2] epilogue -> MMA
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&g.map_a);
+        tma_prefetch_desc(&g.map_b);
+        for (int i = 0; i < C::kStages; ++i) {
+            mbar_init(&full[i], 1);
+            mbar_init(&empty[i], 1);
+        }
+        mbar_init(&tfull[0], 1);
+        mbar_init(&tfull[1], 1);
+        mbar_init(&tempty[0], 4);
+        mbar_init(&tempty[1], 4);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 512);   // 2 accumulator stages x 256 fp32 columns
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int total_tiles = g.tiles_m * g.tiles_n;
+    const int k_iters = g.ntaps * g.k_chunks;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int tn = tile % g.tiles_n;
+                int tm = tile / g.tiles_n;
+                int org[GEMM_MAX_RDIMS];
+#pragma unroll
+                for (int d = 0; d < GEMM_MAX_RDIMS; ++d) {
+                    const int td = g.tdim[d];
+                    org[d] = (tm % td) * g.box[d];
+                    tm /= td;
+                }
+                const int bbatch = g.b_batch_dim >= 0 ? org[g.b_batch_dim] : 0;
+                for (int tap = 0; tap < g.ntaps; ++tap) {
+                    const int c1 = org[0] + g.tap_off[tap][0];
+                    const int c2 = org[1] + g.tap_off[tap][1];
+                    const int c3 = org[2] + g.tap_off[tap][2];
+                    const int c4 = org[3] + g.tap_off[tap][3];
+                    for (int kc = 0; kc < g.k_chunks; ++kc) {
+                        mbar_wait(&empty[stage], phase ^ 1u);
+                        uint8_t* sa = smem + stage * C::kStageBytes;
+                        uint8_t* sb = sa + kABytes;
+                        mbar_expect_tx(&full[stage], static_cast<uint32_t>(g.a_tx_bytes + C::kBBytes));
+                        const int k0 = kc * GEMM_BLOCK_K;
+                        switch (g.nd) {
+                            case 1: tma_load_2d(sa, &g.map_a, &full[stage], k0, c1); break;
+                            case 2: tma_load_3d(sa, &g.map_a, &full[stage], k0, c1, c2); break;
+                            case 3: tma_load_4d(sa, &g.map_a, &full[stage], k0, c1, c2, c3); break;
+                            default: tma_load_5d(sa, &g.map_a, &full[stage], k0, c1, c2, c3, c4); break;
+                        }
+                        tma_load_3d(sb, &g.map_b, &full[stage], k0, tn * BN, tap + bbatch);
+                        if (++stage == C::kStages) {
+                            stage = 0;
+                            phase ^= 1u;
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer
+        constexpr uint32_t idesc = umma_idesc_f16(GEMM_BLOCK_M, BN);
+        int stage = 0;
+        uint32_t phase = 0;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            mbar_wait(&tempty[acc], acc_phase ^ 1u);      // epilogue has drained this accumulator stage
+            tc_fence_after();
+            const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * 256);
+            for (int it = 0; it < k_iters; ++it) {
+                mbar_wait(&full[stage], phase);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t sa = smem_u32(smem + stage * C::kStageBytes);
+                    const uint64_t da = umma_desc_k_sw128(sa);
+                    const uint64_t db = umma_desc_k_sw128(sa + kABytes);
+#pragma unroll
+                    for (int k = 0; k < GEMM_BLOCK_K / 16; ++k) {
+                        // +32 B per K=16 step: start-address field is in 16 B units
+                        umma_f16(tmem_d, da + static_cast<uint64_t>(k * 2), db + static_cast<uint64_t>(k * 2), idesc,
+                                 (it | k) != 0 ? 1u : 0u);
+                    }
+                    umma_commit(&empty[stage]);                       // smem stage reusable once these MMAs retire
+                    if (it == k_iters - 1) umma_commit(&tfull[acc]);  // accumulator complete
+                }
+                __syncwarp();
+                if (++stage == C::kStages) {
+                    stage = 0;
+                    phase ^= 1u;
+                }
+            }
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1u;
+        }
+    } else {
+        // ------------------------------------------------------------------ epilogue (warps 2..5)
+        const int q = warp & 3;                        // TMEM lane quadrant this warp may access
+        const int r = q * 32 + lane;                   // row of the tile held by this thread
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        const bool geglu = (g.flags & GEMM_GEGLU) != 0;
+        const bool out_f32 = (g.flags & GEMM_OUT_F32) != 0;
+        constexpr int CW = BN >= 32 ? 32 : 16;        // columns per tcgen05.ld
+        const int ncols_tile = geglu ? BN / 2 : BN;
+        const bool vec_ok = ((g.ldo & 7) == 0) && ((g.N & 7) == 0) &&
+                            (g.residual == nullptr || (g.ldr & 7) == 0);
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int tn = tile % g.tiles_n;
+            int tm = tile / g.tiles_n;
+            // tile row r -> global row
+            long long grow = 0;
+            long long mul = 1;
+            bool valid = true;
+            {
+                int rr = r;
+#pragma unroll
+                for (int d = 0; d < GEMM_MAX_RDIMS; ++d) {
+                    const int td = g.tdim[d];
+                    const int o = (tm % td) * g.box[d];
+                    tm /= td;
+                    const int i = rr % g.box[d];
+                    rr /= g.box[d];
+                    const int c = o + i;
+                    valid = valid && (c < g.dim[d]);
+                    grow += mul * c;
+                    mul *= g.dim[d];
+                }
+                valid = valid && (rr == 0);
+            }
+            const __half* bias = g.bias;
+            if (bias != nullptr && g.bias_rows > 0) bias += (grow / g.bias_rows) * g.bias_stride;
+
+            mbar_wait(&tfull[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * 256);
+            for (int c0 = 0; c0 < ncols_tile; c0 += CW) {
+                float v[CW];
+                {
+                    uint32_t u[CW];
+                    if constexpr (CW == 32) tmem_ld_32x32(taddr + c0, u);
+                    else tmem_ld_32x16(taddr + c0, u);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < CW; ++j) v[j] = __uint_as_float(u[j]) * g.alpha;
+                }
+                const int pcol = tn * BN + c0;                    // packed (accumulator) column of v[0]
+                if (bias != nullptr) {
+#pragma unroll
+                    for (int j = 0; j < CW; ++j)
+                        if (pcol + j < g.N) v[j] += __half2float(__ldg(bias + pcol + j));
+                }
+                int ocol = pcol;
+                if (geglu) {
+                    float gt[CW];
+                    uint32_t u[CW];
+                    if constexpr (CW == 32) tmem_ld_32x32(taddr + BN / 2 + c0, u);
+                    else tmem_ld_32x16(taddr + BN / 2 + c0, u);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < CW; ++j) {
+                        gt[j] = __uint_as_float(u[j]) * g.alpha;
+                        if (bias != nullptr && pcol + BN / 2 + j < g.N) gt[j] += __half2float(__ldg(bias + pcol + BN / 2 + j));
+                        // reference rounding points (fp16 autocast): proj output, gelu output, product
+                        const float xa = __half2float(__float2half_rn(v[j]));
+                        const float ga = __half2float(__float2half_rn(gt[j]));
+                        const float ge = __half2float(__float2half_rn(gelu_erf(ga)));
+                        v[j] = xa * ge;
+                    }
+                    ocol = tn * (BN / 2) + c0;
+                }
+                const int nvalid = geglu ? g.N / 2 : g.N;
+                if (valid) {
+                    if (g.residual != nullptr) {
+                        const __half* rp = g.residual + grow * g.ldr + ocol;
+                        if (vec_ok) {
+#pragma unroll
+                            for (int j = 0; j < CW; j += 8) {
+                                if (ocol + j < nvalid) {
+                                    const uint4 rv = __ldg(reinterpret_cast<const uint4*>(rp + j));
+                                    const __half2* h2 = reinterpret_cast<const __half2*>(&rv);
+#pragma unroll
+                                    for (int e = 0; e < 4; ++e) {
+                                        const float2 f = __half22float2(h2[e]);
+                                        v[j + 2 * e] += f.x;
+                                        v[j + 2 * e + 1] += f.y;
+                                    }
+                                }
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < CW; ++j)
+                                if (ocol + j < nvalid) v[j] += __half2float(rp[j]);
+                        }
+                    }
+                    if (out_f32) {
+                        float* op = reinterpret_cast<float*>(g.out) + grow * g.ldo + ocol;
+#pragma unroll
+                        for (int j = 0; j < CW; ++j)
+                            if (ocol + j < nvalid) op[j] = v[j];
+                    } else {
+                        __half* op = reinterpret_cast<__half*>(g.out) + grow * g.ldo + ocol;
+                        if (vec_ok) {
+#pragma unroll
+                            for (int j = 0; j < CW; j += 8) {
+                                if (ocol + j < nvalid) {
+                                    uint4 ov;
+                                    __half2* h2 = reinterpret_cast<__half2*>(&ov);
+#pragma unroll
+                                    for (int e = 0; e < 4; ++e) h2[e] = __floats2half2_rn(v[j + 2 * e], v[j + 2 * e + 1]);
+                                    *reinterpret_cast<uint4*>(op + j) = ov;
+                                }
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < CW; ++j)
+                                if (ocol + j < nvalid) op[j] = __float2half_rn(v[j]);
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc]);
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1u;
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// ------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode = nullptr;
+bool g_inited = false;
+
+int encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+               const cuuint32_t* box) {
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, static_cast<cuuint32_t>(rank), const_cast<void*>(base),
+                          dims, strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        fprintf(stderr, "[t2v_b200] cuTensorMapEncodeTiled failed: %d (rank %d, dims %llu %llu %llu %llu %llu)\n",
+                static_cast<int>(r), rank, (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0),
+                (unsigned long long)(rank > 2 ? dims[2] : 0), (unsigned long long)(rank > 3 ? dims[3] : 0),
+                (unsigned long long)(rank > 4 ? dims[4] : 0));
+        return -1;
+    }
+    return 0;
+}
+
+template <int BN>
+int set_attr() {
+    return cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                Cfg<BN>::kSmemBytes) == cudaSuccess ? 0 : -1;
+}
+
+}  // namespace
+
+int gemm_init() {
+    if (g_inited) return 0;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess ||
+        fn == nullptr) {
+        fprintf(stderr, "[t2v_b200] cuTensorMapEncodeTiled entry point not found\n");
+        return -1;
+    }
+    g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+    if (set_attr<16>() || set_attr<64>() || set_attr<128>() || set_attr<160>() || set_attr<256>()) {
+        fprintf(stderr, "[t2v_b200] cudaFuncSetAttribute(max dynamic smem) failed: %s\n",
+                cudaGetErrorString(cudaGetLastError()));
+        return -1;
+    }
+    g_inited = true;
+    return 0;
+}
+
+int gemm_plan(const GemmProblem& p, GemmPlan* plan, int num_sms) {
+    if (gemm_init() != 0) return -1;
+    if (p.nd < 1 || p.nd > GEMM_MAX_RDIMS || p.ntaps < 1 || p.ntaps > GEMM_MAX_TAPS) return -2;
+    if ((p.lda & 7) != 0 || (p.K & 7) != 0 || (reinterpret_cast<uintptr_t>(p.a) & 15) != 0 ||
+        (reinterpret_cast<uintptr_t>(p.b) & 15) != 0) {
+        fprintf(stderr, "[t2v_b200] gemm_plan: operands must be 16-byte aligned (lda %lld K %d)\n", p.lda, p.K);
+        return -3;
+    }
+    GemmDesc& g = plan->desc;
+    memset(&g, 0, sizeof(g));
+    g.nd = p.nd;
+    long long rows = 1;
+    // ---- M tiling: fill a 128-row box from the fastest row dim outwards
+    int remaining = GEMM_BLOCK_M;
+    int boxrows = 1;
+    for (int d = 0; d < GEMM_MAX_RDIMS; ++d) {
+        const int ext = d < p.nd ? p.dim[d] : 1;
+        g.dim[d] = ext;
+        int b = std::min(ext, remaining);
+        if (b < 1) b = 1;
+        // keep boxes that do not cover a full dim a divisor-friendly size (avoid ragged interior tiles)
+        g.box[d] = b;
+        g.tdim[d] = (ext + b - 1) / b;
+        remaining = b >= ext ? remaining / b : 1;     // only grow into the next dim when this one is fully covered
+        boxrows *= b;
+        rows *= ext;
+    }
+    if (p.b_batch_dim >= 0 && g.box[p.b_batch_dim] != 1) {
+        // a tile may not straddle two B batches: shrink that dim's box to 1
+        const int d = p.b_batch_dim;
+        boxrows /= g.box[d];
+        g.box[d] = 1;
+        g.tdim[d] = g.dim[d];
+        for (int e = d + 1; e < GEMM_MAX_RDIMS; ++e) {   // outer dims were grown assuming d was covered
+            boxrows /= g.box[e];
+            g.box[e] = 1;
+            g.tdim[e] = g.dim[e];
+        }
+    }
+    g.tiles_m = 1;
+    for (int d = 0; d < GEMM_MAX_RDIMS; ++d) g.tiles_m *= g.tdim[d];
+    g.a_tx_bytes = boxrows * GEMM_BLOCK_K * 2;
+    g.ntaps = p.ntaps;
+    g.k_chunks = (p.K + GEMM_BLOCK_K - 1) / GEMM_BLOCK_K;
+    for (int t = 0; t < p.ntaps; ++t)
+        for (int d = 0; d < GEMM_MAX_RDIMS; ++d) g.tap_off[t][d] = static_cast<int8_t>(d < p.nd ? p.tap_off[t][d] : 0);
+    g.b_batch_dim = p.b_batch_dim;
+    g.N = p.N;
+    g.flags = p.flags;
+    g.out = p.out;
+    g.ldo = p.ldo;
+    g.bias = p.bias;
+    g.bias_rows = p.bias_rows;
+    g.bias_stride = p.bias_stride;
+    g.residual = p.residual;
+    g.ldr = p.ldr;
+    g.alpha = p.alpha == 0.f ? 1.0f : p.alpha;
+
+    // ---- N tiling: widest tile that keeps the machine full
+    int bn = p.force_bn;
+    if (bn == 0) {
+        const int cands[5] = {256, 160, 128, 64, 16};
+        const double eff[5] = {1.0, 0.97, 0.92, 0.70, 0.25};
+        double best = -1;
+        for (int i = 0; i < 5; ++i) {
+            const int c = cands[i];
+            if ((p.flags & GEMM_GEGLU) && c != 256 && c != 128 && c != 64) continue;
+            if (c == 16 && p.N > 16) continue;
+            if (c > 16 && p.N <= 16) continue;
+            const int tn = (p.N + c - 1) / c;
+            const double waste = static_cast<double>(p.N) / (static_cast<double>(tn) * c);
+            const long long tiles = static_cast<long long>(tn) * g.tiles_m;
+            const long long waves = (tiles + num_sms - 1) / num_sms;
+            const double fill = static_cast<double>(tiles) / (static_cast<double>(waves) * num_sms);
+            const double score = eff[i] * waste * fill;
+            if (score > best) {
+                best = score;
+                bn = c;
+            }
+        }
+    }
+    plan->bn = bn;
+    g.tiles_n = (p.N + bn - 1) / bn;
+    if ((p.flags & GEMM_GEGLU) && (p.N % bn) != 0) {
+        fprintf(stderr, "[t2v_b200] gemm_plan: GEGLU needs N %% BN == 0 (N %d BN %d)\n", p.N, bn);
+        return -4;
+    }
+
+    // ---- tensor maps
+    {
+        cuuint64_t dims[5], strides[4];
+        cuuint32_t box[5];
+        dims[0] = static_cast<cuuint64_t>(p.K);
+        box[0] = GEMM_BLOCK_K;
+        long long pitch = p.lda * 2;       // bytes between consecutive rows
+        for (int d = 0; d < p.nd; ++d) {
+            dims[d + 1] = static_cast<cuuint64_t>(g.dim[d]);
+            box[d + 1] = static_cast<cuuint32_t>(g.box[d]);
+            strides[d] = static_cast<cuuint64_t>(pitch);
+            pitch *= g.dim[d];
+        }
+        if (encode_map(&g.map_a, p.a, p.nd + 1, dims, strides, box) != 0) return -5;
+    }
+    {
+        const int nb = p.b_batch_dim >= 0 ? g.dim[p.b_batch_dim] : p.ntaps;
+        cuuint64_t dims[3] = {static_cast<cuuint64_t>(p.K), static_cast<cuuint64_t>(p.n_alloc),
+                              static_cast<cuuint64_t>(nb)};
+        cuuint64_t strides[2] = {static_cast<cuuint64_t>(p.K) * 2,
+                                 static_cast<cuuint64_t>(p.K) * 2 * static_cast<cuuint64_t>(p.n_alloc)};
+        cuuint32_t box[3] = {GEMM_BLOCK_K, static_cast<cuuint32_t>(bn), 1};
+        if (encode_map(&g.map_b, p.b, 3, dims, strides, box) != 0) return -6;
+    }
+    const long long total = static_cast<long long>(g.tiles_m) * g.tiles_n;
+    plan->grid = static_cast<int>(std::min<long long>(total, num_sms));
+    switch (bn) {
+        case 16: plan->smem = Cfg<16>::kSmemBytes; break;
+        case 64: plan->smem = Cfg<64>::kSmemBytes; break;
+        case 128: plan->smem = Cfg<128>::kSmemBytes; break;
+        case 160: plan->smem = Cfg<160>::kSmemBytes; break;
+        case 256: plan->smem = Cfg<256>::kSmemBytes; break;
+        default: return -7;
+    }
+    plan->flops = 2.0 * static_cast<double>(rows) * p.N * p.K * p.ntaps;
+    return 0;
+}
+
+int gemm_launch(const GemmPlan& plan, cudaStream_t stream) {
+    switch (plan.bn) {
+        case 16: gemm_tc_kernel<16><<<plan.grid, kThreads, plan.smem, stream>>>(plan.desc); break;
+        case 64: gemm_tc_kernel<64><<<plan.grid, kThreads, plan.smem, stream>>>(plan.desc); break;
+        case 128: gemm_tc_kernel<128><<<plan.grid, kThreads, plan.smem, stream>>>(plan.desc); break;
+        case 160: gemm_tc_kernel<160><<<plan.grid, kThreads, plan.smem, stream>>>(plan.desc); break;
+        case 256: gemm_tc_kernel<256><<<plan.grid, kThreads, plan.smem, stream>>>(plan.desc); break;
+        default: return -1;
+    }
+    return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
+}  // namespace t2v

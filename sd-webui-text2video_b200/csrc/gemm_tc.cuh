@@ -1,0 +1,90 @@
+// Implicit-GEMM engine on tcgen05: every dense contraction of the denoiser / VAE (Linear, Conv1d k=1,
+// Conv2d 1x1 / 3x3, Conv3d (3,1,1)) is one launch of gemm_tc_kernel.
+//
+//   D[row, n] = sum_{tap} sum_{k} A[row + tap_offset(tap), k] * W[tap][n][k]   (+ bias, + residual, GEGLU ...)
+//
+// Activations live channels-last in HBM: A is a [rows, C] fp16 matrix whose rows are the (sample, frame, y, x)
+// tokens.  A TMA tensor map of rank 1+nd views the rows as an nd-dimensional grid (e.g. C,w,h,F,B); a "tap" is
+// an integer offset in that grid, and TMA's out-of-bounds zero fill IS the convolution's zero padding -- no
+// im2col buffer, no transposes.  Weights are packed once as W[tap][N][K] (K-major).
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace t2v {
+
+constexpr int GEMM_BLOCK_M = 128;
+constexpr int GEMM_BLOCK_K = 64;     // 64 fp16 = 128 B = one SWIZZLE_128B row
+constexpr int GEMM_MAX_TAPS = 9;
+constexpr int GEMM_MAX_RDIMS = 4;
+
+enum GemmFlags : int {
+    GEMM_GEGLU = 1,        // epilogue: out[:, j] = (acc[:, j] + b) * gelu(acc[:, BN/2 + j] + b)  (weights interleaved per tile)
+    GEMM_OUT_F32 = 2,      // store fp32 instead of fp16
+};
+
+struct GemmDesc {
+    CUtensorMap map_a;               // rank 1 + nd : (K, d0, d1, ...)
+    CUtensorMap map_b;               // rank 3      : (K, N, taps | batch)
+    int nd;                          // number of row dims (1..4)
+    int dim[GEMM_MAX_RDIMS];         // extent of each row dim (d0 fastest)
+    int box[GEMM_MAX_RDIMS];         // rows-box extent per dim; prod(box) <= 128
+    int tdim[GEMM_MAX_RDIMS];        // tiles per dim
+    int tiles_m, tiles_n;
+    int ntaps, k_chunks;
+    int8_t tap_off[GEMM_MAX_TAPS][GEMM_MAX_RDIMS];
+    int b_batch_dim;                 // >=0: B coordinate 2 = tile origin along that row dim (batched GEMM)
+    int a_tx_bytes;                  // bytes one A box load deposits
+    int N;                           // valid output columns (GEGLU: of the packed 2x-wide accumulator)
+    int flags;
+    void* out;
+    long long ldo;                   // output row pitch (elements)
+    const __half* bias;              // [N] (packed order) or null
+    int bias_rows;                   // >0: bias row = global_row / bias_rows (per-sample bias, e.g. time-embedding)
+    long long bias_stride;
+    const __half* residual;          // [rows, ldr] or null
+    long long ldr;
+    float alpha;                     // accumulator scale applied before bias (1.0 normally)
+};
+
+struct GemmProblem {
+    const __half* a;
+    long long lda;                   // row pitch of A in elements (>= K, multiple of 8)
+    int K;                           // channels per tap
+    int nd;
+    int dim[GEMM_MAX_RDIMS];
+    int ntaps;
+    int tap_off[GEMM_MAX_TAPS][GEMM_MAX_RDIMS];
+    const __half* b;                 // packed [taps or batch][n_alloc][K]
+    int n_alloc;                     // allocated rows per tap in b (>= N, allows padding for tiny N)
+    int N;
+    int b_batch_dim;                 // -1 if none
+    int flags;
+    void* out;
+    long long ldo;
+    const __half* bias;
+    int bias_rows;
+    long long bias_stride;
+    const __half* residual;
+    long long ldr;
+    float alpha;
+    int force_bn;                    // 0 = auto
+};
+
+struct GemmPlan {
+    GemmDesc desc;
+    int bn;
+    int grid;
+    int smem;
+    double flops;
+};
+
+// Builds tensor maps / tile shapes for a problem.  Returns 0 on success.
+int gemm_plan(const GemmProblem& p, GemmPlan* plan, int num_sms);
+int gemm_launch(const GemmPlan& plan, cudaStream_t stream);
+// One-time: cudaFuncSetAttribute for all instantiations + driver entry point lookup.
+int gemm_init();
+
+}  // namespace t2v

@@ -1,0 +1,246 @@
+// GroupNorm (32 groups) statistics + apply(+SiLU), and LayerNorm, on channels-last fp16 token matrices.
+// HBM-bound kernels: algorithmic bytes = 2 B/element read for stats, 2 B read + 2 B write for apply.
+//
+// Reduction domains: 4-D GroupNorm = one frame (h*w rows); 5-D GroupNorm = one sample
+// (F*h*w rows).  Both are "instances" of `rows_per_inst` consecutive rows here.
+// fp32 math throughout (the reference runs group_norm / layer_norm / SiLU-after-norm in fp32 under autocast and
+// rounds to fp16 only when the value enters the next conv/linear -- exactly where these kernels round).
+#include "kernels.cuh"
+
+namespace t2v {
+
+namespace {
+
+constexpr int kGroups = 32;
+constexpr int kStatsThreads = 256;   // 32 vector lanes (x) x 8 row lanes (y)
+
+// partial[(inst * nchunks + chunk) * 32 + g] = (sum, sumsq) ; the last block of an instance folds them (in
+// chunk order, double precision) into stats[inst*32+g] = (mean, rstd) -> deterministic, no float atomics in HBM.
+__global__ void __launch_bounds__(kStatsThreads) gn_stats_kernel(const __half* __restrict__ x, long long ld, int C,
+                                                                 int rows_per_inst, int rows_per_chunk, int nchunks,
+                                                                 float eps, float2* __restrict__ partial,
+                                                                 unsigned int* __restrict__ counters,
+                                                                 float2* __restrict__ stats) {
+    extern __shared__ float sm[];          // [2*C] per-channel sum / sumsq
+    float* s_sum = sm;
+    float* s_sq = sm + C;
+    __shared__ bool is_last;
+    const int inst = blockIdx.y;
+    const int chunk = blockIdx.x;
+    const int tx = threadIdx.x & 31;
+    const int ty = threadIdx.x >> 5;
+    const int C8 = C >> 3;
+    for (int i = threadIdx.x; i < 2 * C; i += kStatsThreads) sm[i] = 0.f;
+    __syncthreads();
+    const int r0 = chunk * rows_per_chunk;
+    const int r1 = min(r0 + rows_per_chunk, rows_per_inst);
+    const __half* base = x + static_cast<long long>(inst) * rows_per_inst * ld;
+    for (int vc = tx; vc < C8; vc += 32) {
+        float s[8], q[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) s[e] = q[e] = 0.f;
+        for (int r = r0 + ty; r < r1; r += 8) {
+            const uint4 v = __ldg(reinterpret_cast<const uint4*>(base + r * ld + vc * 8));
+            const __half2* h2 = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float2 f = __half22float2(h2[e]);
+                s[2 * e] += f.x;
+                q[2 * e] += f.x * f.x;
+                s[2 * e + 1] += f.y;
+                q[2 * e + 1] += f.y * f.y;
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            atomicAdd(&s_sum[vc * 8 + e], s[e]);
+            atomicAdd(&s_sq[vc * 8 + e], q[e]);
+        }
+    }
+    __syncthreads();
+    const int cpg = C / kGroups;
+    if (threadIdx.x < kGroups) {
+        float a = 0.f, b = 0.f;
+        for (int c = 0; c < cpg; ++c) {
+            a += s_sum[threadIdx.x * cpg + c];
+            b += s_sq[threadIdx.x * cpg + c];
+        }
+        partial[(static_cast<long long>(inst) * nchunks + chunk) * kGroups + threadIdx.x] = make_float2(a, b);
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int prev = atomicAdd(&counters[inst], 1u);
+        is_last = (prev == static_cast<unsigned int>(nchunks - 1));
+    }
+    __syncthreads();
+    if (is_last) {
+        __threadfence();
+        if (threadIdx.x < kGroups) {
+            double a = 0.0, b = 0.0;
+            for (int ch = 0; ch < nchunks; ++ch) {
+                const float2 p = partial[(static_cast<long long>(inst) * nchunks + ch) * kGroups + threadIdx.x];
+                a += p.x;
+                b += p.y;
+            }
+            const double n = static_cast<double>(rows_per_inst) * cpg;
+            const double mean = a / n;
+            double var = b / n - mean * mean;
+            if (var < 0.0) var = 0.0;
+            stats[inst * kGroups + threadIdx.x] =
+                make_float2(static_cast<float>(mean), static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps))));
+        }
+        if (threadIdx.x == 0) counters[inst] = 0u;     // self-cleaning for the next launch
+    }
+}
+
+__device__ __forceinline__ float silu_f(float v) { return v / (1.0f + __expf(-v)); }
+
+__global__ void __launch_bounds__(256) gn_apply_kernel(const __half* __restrict__ x, long long ldx,
+                                                       __half* __restrict__ y, long long ldy, long long rows, int C,
+                                                       int rows_per_inst, const float2* __restrict__ stats,
+                                                       const __half* __restrict__ gamma,
+                                                       const __half* __restrict__ beta, int silu) {
+    const int C8 = C >> 3;
+    const int cpg = C / kGroups;
+    const long long total = rows * C8;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long r = i / C8;
+        const int vc = static_cast<int>(i - r * C8);
+        const int inst = static_cast<int>(r / rows_per_inst);
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(x + r * ldx + vc * 8));
+        const uint4 gv = __ldg(reinterpret_cast<const uint4*>(gamma + vc * 8));
+        const uint4 bv = __ldg(reinterpret_cast<const uint4*>(beta + vc * 8));
+        const __half* xh = reinterpret_cast<const __half*>(&v);
+        const __half* gh = reinterpret_cast<const __half*>(&gv);
+        const __half* bh = reinterpret_cast<const __half*>(&bv);
+        uint4 o;
+        __half* oh = reinterpret_cast<__half*>(&o);
+        const float2* st = stats + inst * kGroups;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const float2 ms = __ldg(st + (vc * 8 + e) / cpg);
+            float f = (__half2float(xh[e]) - ms.x) * ms.y * __half2float(gh[e]) + __half2float(bh[e]);
+            if (silu) f = silu_f(f);
+            oh[e] = __float2half_rn(f);
+        }
+        *reinterpret_cast<uint4*>(y + r * ldy + vc * 8) = o;
+    }
+}
+
+// one warp per row; C <= 2048, C % 8 == 0
+__global__ void __launch_bounds__(256) layernorm_kernel(const __half* __restrict__ x, long long ldx,
+                                                        __half* __restrict__ y, long long ldy, long long rows, int C,
+                                                        const __half* __restrict__ gamma,
+                                                        const __half* __restrict__ beta, float eps) {
+    const int lane = threadIdx.x & 31;
+    const long long row = blockIdx.x * static_cast<long long>(blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int C8 = C >> 3;
+    constexpr int MAXV = 8;
+    uint4 v[MAXV];
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < MAXV; ++k) {
+        const int vc = lane + k * 32;
+        if (vc < C8) {
+            v[k] = __ldg(reinterpret_cast<const uint4*>(x + row * ldx + vc * 8));
+            const __half2* h2 = reinterpret_cast<const __half2*>(&v[k]);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float2 f = __half22float2(h2[e]);
+                s += f.x + f.y;
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s / C;
+    float q = 0.f;
+#pragma unroll
+    for (int k = 0; k < MAXV; ++k) {
+        const int vc = lane + k * 32;
+        if (vc < C8) {
+            const __half2* h2 = reinterpret_cast<const __half2*>(&v[k]);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float2 f = __half22float2(h2[e]);
+                q += (f.x - mean) * (f.x - mean) + (f.y - mean) * (f.y - mean);
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float rstd = rsqrtf(q / C + eps);
+#pragma unroll
+    for (int k = 0; k < MAXV; ++k) {
+        const int vc = lane + k * 32;
+        if (vc < C8) {
+            const uint4 gv = __ldg(reinterpret_cast<const uint4*>(gamma + vc * 8));
+            const uint4 bv = __ldg(reinterpret_cast<const uint4*>(beta + vc * 8));
+            const __half* xh = reinterpret_cast<const __half*>(&v[k]);
+            const __half* gh = reinterpret_cast<const __half*>(&gv);
+            const __half* bh = reinterpret_cast<const __half*>(&bv);
+            uint4 o;
+            __half* oh = reinterpret_cast<__half*>(&o);
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+                oh[e] = __float2half_rn((__half2float(xh[e]) - mean) * rstd * __half2float(gh[e]) + __half2float(bh[e]));
+            *reinterpret_cast<uint4*>(y + row * ldy + vc * 8) = o;
+        }
+    }
+}
+
+}  // namespace
+
+int gn_rows_per_chunk(int rows_per_inst, int n_inst, int num_sms) {
+    // aim for >= ~4 blocks per SM, chunks of at least 8 rows
+    long long want = static_cast<long long>(num_sms) * 4;
+    long long chunks_per_inst = (want + n_inst - 1) / n_inst;
+    if (chunks_per_inst < 1) chunks_per_inst = 1;
+    long long rpc = (rows_per_inst + chunks_per_inst - 1) / chunks_per_inst;
+    if (rpc < 8) rpc = 8;
+    rpc = (rpc + 7) / 8 * 8;
+    return static_cast<int>(rpc);
+}
+
+size_t gn_workspace_bytes(int rows_per_inst, int n_inst, int num_sms) {
+    const int rpc = gn_rows_per_chunk(rows_per_inst, n_inst, num_sms);
+    const int nchunks = (rows_per_inst + rpc - 1) / rpc;
+    // partials + stats + counters
+    return static_cast<size_t>(n_inst) * nchunks * kGroups * sizeof(float2) + static_cast<size_t>(n_inst) * kGroups * sizeof(float2) +
+           static_cast<size_t>(n_inst) * sizeof(unsigned int) + 256;
+}
+
+int groupnorm_silu(const __half* x, long long ldx, __half* y, long long ldy, long long rows, int C, int rows_per_inst,
+                   const __half* gamma, const __half* beta, float eps, int silu, void* workspace, int num_sms,
+                   cudaStream_t stream) {
+    if (C % 32 != 0 || C % 8 != 0 || rows % rows_per_inst != 0) return -1;
+    const int n_inst = static_cast<int>(rows / rows_per_inst);
+    const int rpc = gn_rows_per_chunk(rows_per_inst, n_inst, num_sms);
+    const int nchunks = (rows_per_inst + rpc - 1) / rpc;
+    uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+    float2* partial = reinterpret_cast<float2*>(ws);
+    float2* stats = partial + static_cast<size_t>(n_inst) * nchunks * kGroups;
+    unsigned int* counters = reinterpret_cast<unsigned int*>(stats + static_cast<size_t>(n_inst) * kGroups);
+    gn_stats_kernel<<<dim3(nchunks, n_inst), kStatsThreads, 2 * C * sizeof(float), stream>>>(
+        x, ldx, C, rows_per_inst, rpc, nchunks, eps, partial, counters, stats);
+    const long long total = rows * (C / 8);
+    long long blocks = (total + 255) / 256;
+    const long long cap = static_cast<long long>(num_sms) * 16;
+    if (blocks > cap) blocks = cap;
+    gn_apply_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(x, ldx, y, ldy, rows, C, rows_per_inst, stats, gamma,
+                                                                  beta, silu);
+    return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
+int layernorm(const __half* x, long long ldx, __half* y, long long ldy, long long rows, int C, const __half* gamma,
+              const __half* beta, float eps, cudaStream_t stream) {
+    if (C % 8 != 0 || C > 2048) return -1;
+    const long long blocks = (rows + 7) / 8;
+    layernorm_kernel<<<static_cast<unsigned int>(blocks), 256, 0, stream>>>(x, ldx, y, ldy, rows, C, gamma, beta, eps);
+    return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
+}  // namespace t2v

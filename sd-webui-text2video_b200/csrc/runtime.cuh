@@ -1,0 +1,115 @@
+// Host runtime shared by the denoiser and the VAE decoder: parameter store, packed-weight cache, a lifetime-aware
+// activation arena, and the "plan" -- a flat list of pre-encoded kernel launches (tensor maps encoded once per
+// shape) that one forward replays on a stream without any host-side shape logic.
+#pragma once
+#include "common.cuh"
+#include "gemm_tc.cuh"
+#include "kernels.cuh"
+
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <functional>
+#include <map>
+#include <string>
+#include <vector>
+
+namespace t2v {
+
+// ----------------------------------------------------------------------------------------- parameters
+struct Param {
+    std::vector<long long> shape;
+    __half* data = nullptr;      // fp16 copy in the ORIGINAL (PyTorch) layout, library-owned
+    long long elems = 0;
+    bool expected = false;
+    bool set = false;
+};
+
+class ParamStore {
+public:
+    ~ParamStore();
+    void expect(const std::string& name, std::vector<long long> shape);
+    int set(const std::string& name, const void* src, int dtype, int ndim, const int64_t* shape, cudaStream_t s);
+    int missing(std::string* one) const;
+    const Param& get(const std::string& name) const;     // aborts via set_error + null data if absent
+    bool has(const std::string& name) const { return params_.count(name) != 0; }
+    // packed variants, created lazily and cached until any parameter changes
+    __half* packed(const std::string& key) const;
+    __half* new_packed(const std::string& key, long long elems);
+    void invalidate_packed();
+    unsigned long long version() const { return version_; }
+
+private:
+    std::map<std::string, Param> params_;
+    std::map<std::string, __half*> packed_;
+    unsigned long long version_ = 0;
+};
+
+// ----------------------------------------------------------------------------------------- arena
+// Offsets are handed out by a first-fit free list while the plan is being built (the build order IS the execution
+// order, so build-time lifetimes are run-time lifetimes).  A dry pass measures the peak, then the real pass runs
+// against one cudaMalloc'ed slab.
+class Arena {
+public:
+    void reset(char* base, bool no_reuse);
+    char* alloc(size_t bytes);
+    void free(char* p);
+    size_t peak() const { return peak_; }
+
+private:
+    struct Blk { size_t off, size; };
+    char* base_ = nullptr;
+    bool no_reuse_ = false;
+    size_t top_ = 0, peak_ = 0;
+    std::vector<Blk> free_;
+    std::map<size_t, size_t> live_;
+};
+
+struct Tok {                      // channels-last token matrix view
+    __half* p = nullptr;
+    long long rows = 0;
+    int C = 0;
+    long long ld = 0;
+};
+
+using Step = std::function<int(cudaStream_t)>;
+
+struct Plan {
+    std::vector<Step> steps;
+    char* slab = nullptr;
+    size_t slab_bytes = 0;
+    double flops = 0.0;
+    int launches = 0;
+    unsigned long long weights_version = 0;
+    std::map<std::string, std::pair<Tok, std::pair<int, int>>> taps;    // name -> (tokens, (h, w))
+    cudaGraphExec_t graph = nullptr;
+    ~Plan();
+};
+
+// Helper that records launches into a plan (or only simulates allocations when `dry`).
+class Builder {
+public:
+    Builder(Plan* plan, Arena* arena, bool dry, int sms) : plan_(plan), arena_(arena), dry_(dry), sms_(sms) {}
+    bool dry() const { return dry_; }
+    Tok alloc(long long rows, int C, int ld = 0);
+    void* alloc_bytes(size_t bytes);
+    void free(const Tok& t) { arena_->free(reinterpret_cast<char*>(t.p)); }
+    void free_bytes(void* p) { arena_->free(reinterpret_cast<char*>(p)); }
+    int gemm(GemmProblem& p);                                     // plans + records; returns 0 or <0
+    void step(Step s, int launches = 1);
+    void add_flops(double f) { plan_->flops += f; }
+    int sms() const { return sms_; }
+    int error = 0;
+
+private:
+    Plan* plan_;
+    Arena* arena_;
+    bool dry_;
+    int sms_;
+};
+
+// conv taps helpers over row dims (w, h, frames) and (pixels, frames, samples)
+void taps_3x3(GemmProblem& p);
+void taps_temporal(GemmProblem& p);
+
+}  // namespace t2v
