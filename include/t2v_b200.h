@@ -55,6 +55,10 @@ int t2v_unet_set_param(t2v_unet* u, const char* name, const void* data, int dtyp
                        void* stream);
 /* Number of parameters still missing (0 => ready); fills `name_out` with one missing key if non-null. */
 int t2v_unet_missing_params(t2v_unet* u, char* name_out, size_t name_cap);
+/* Enumerates the expected state_dict: index in [0, count) -> key name + shape (shape has room for 8 dims).
+ * Returns the number of expected parameters, or -1 if `index` is out of range.  The Python mirror builds its
+ * nn.Module tree (same names, nn.Linear / nn.Conv2d / nn.Conv3d leaves) from this list.                     */
+int t2v_unet_param_info(t2v_unet* u, int index, char* name_out, size_t name_cap, int64_t* shape_out, int* ndim_out);
 /* eps = UNetSD.forward(x, t, y) (t2v_model.py:386-459).
  *   x   [B, in_dim, F, h, w]  fp32 (x_is_f32 = 1) or fp16, NCFHW exactly as the samplers hold the latent
  *   t   [B] float32 (host converts int64 timesteps; UniPC already passes floats, uni_pc.py:248)
@@ -89,6 +93,7 @@ void t2v_vae_destroy(t2v_vae* v);
 int t2v_vae_set_param(t2v_vae* v, const char* name, const void* data, int dtype, int ndim, const int64_t* shape,
                       void* stream);
 int t2v_vae_missing_params(t2v_vae* v, char* name_out, size_t name_cap);
+int t2v_vae_param_info(t2v_vae* v, int index, char* name_out, size_t name_cap, int64_t* shape_out, int* ndim_out);
 /* z [B, z_channels, F, h, w] fp32/fp16 latent as returned by the sampler; multiplied by `z_scale`
  * (1/0.18215, t2v_pipeline.py:348) on ingest.
  *   out_mode 0: float32 [B*F, 3, 8h, 8w] in [-1, 1]   (what AutoencoderKL.decode returns, per frame)
@@ -100,11 +105,12 @@ double t2v_vae_flops(t2v_vae* v, int nframes, int h, int w);
 /* ------------------------------------------------------------------------------------------ sampler steps
  * replace the per-step tensor arithmetic of scripts/samplers (ddim/gaussian_sampler.py:125-136,:269-283;
  * ddim/sampler.py:176-218; uni_pc/uni_pc.py:299-307,:378-391,:625-650).                                  */
-int t2v_ddim_step(const float* x, const void* eps_c, const void* eps_u, float* x_out, long long n, long long chan_stride,
+int t2v_ddim_step(const float* x, const void* eps_c, const void* eps_u, int eps_is_f32, float* x_out, long long n,
+                  long long chan_stride,
                   int C, int guided_channels, float g, int mode, float a0, float a1, float a2, float a3, float a4,
                   const float* noise, int cfg_fp16, void* stream);
-int t2v_cfg_x0(const float* x, const void* eps_c, const void* eps_u, float* x0, long long n, float g, float alpha,
-               float sigma, int cfg_fp16, void* stream);
+int t2v_cfg_x0(const float* x, const void* eps_c, const void* eps_u, int eps_is_f32, float* x0, long long n, float g,
+               float alpha, float sigma, int cfg_fp16, void* stream);
 int t2v_lincomb(float* out, const float* const* src, const float* coef, int n_src, long long n, void* stream);
 
 /* ------------------------------------------------------------------------------------------ kernel-level entry

@@ -182,7 +182,7 @@ def analytic_model(x, t, c):
     """Cheap deterministic eps-model used to pin the schedulers without a UNet."""
     tt = t.float().view(-1, *((1,) * (x.ndim - 1))) / 1000.0
     bias = c.float().mean() if c is not None else 0.0
-    ch = torch.arange(x.shape[1], dtype=x.dtype).view(1, -1, *((1,) * (x.ndim - 2)))
+    ch = torch.arange(x.shape[1], dtype=x.dtype, device=x.device).view(1, -1, *((1,) * (x.ndim - 2)))
     return (torch.tanh(0.8 * x + 0.5 * tt + 0.1 * ch) * 0.9 + 0.3 * bias + 0.05 * torch.roll(x, 1, dims=2)).to(x.dtype)
 
 

@@ -164,18 +164,18 @@ int t2v_op_small_linear(const void* x, long long ldx, const void* W, const void*
                         reinterpret_cast<const __half*>(bias), reinterpret_cast<const __half*>(addend),
                         reinterpret_cast<__half*>(y), ldy, B, N, K, silu_in, reinterpret_cast<cudaStream_t>(stream));
 }
-int t2v_ddim_step(const float* x, const void* eps_c, const void* eps_u, float* x_out, long long n, long long chan_stride,
+int t2v_ddim_step(const float* x, const void* eps_c, const void* eps_u, int eps_is_f32, float* x_out, long long n, long long chan_stride,
                   int C, int guided_channels, float g, int mode, float a0, float a1, float a2, float a3, float a4,
                   const float* noise, int cfg_fp16, void* stream) {
     DdimStepParams p;
-    p.x = x; p.eps_c = reinterpret_cast<const __half*>(eps_c); p.eps_u = reinterpret_cast<const __half*>(eps_u);
+    p.x = x; p.eps_c = eps_c; p.eps_u = eps_u; p.eps_is_f32 = eps_is_f32;
     p.x_out = x_out; p.n = n; p.chan_stride = chan_stride; p.C = C; p.guided_channels = guided_channels; p.g = g;
     p.mode = mode; p.a0 = a0; p.a1 = a1; p.a2 = a2; p.a3 = a3; p.a4 = a4; p.noise = noise; p.cfg_fp16 = cfg_fp16;
     return ddim_step(p, reinterpret_cast<cudaStream_t>(stream));
 }
-int t2v_cfg_x0(const float* x, const void* eps_c, const void* eps_u, float* x0, long long n, float g, float alpha,
+int t2v_cfg_x0(const float* x, const void* eps_c, const void* eps_u, int eps_is_f32, float* x0, long long n, float g, float alpha,
                float sigma, int cfg_fp16, void* stream) {
-    return cfg_x0(x, reinterpret_cast<const __half*>(eps_c), reinterpret_cast<const __half*>(eps_u), x0, n, g, alpha, sigma,
+    return cfg_x0(x, eps_c, eps_u, eps_is_f32, x0, n, g, alpha, sigma,
                   cfg_fp16, reinterpret_cast<cudaStream_t>(stream));
 }
 int t2v_lincomb(float* out, const float* const* src, const float* coef, int n_src, long long n, void* stream) {

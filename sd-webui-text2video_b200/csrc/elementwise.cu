@@ -265,12 +265,16 @@ __device__ __forceinline__ float cfg_combine(float c, float u, float g, int fp16
     return __fadd_rn(u, __fmul_rn(g, __fsub_rn(c, u)));
 }
 
+__device__ __forceinline__ float load_eps(const void* p, long long i, int is_f32) {
+    return is_f32 ? reinterpret_cast<const float*>(p)[i] : __half2float(reinterpret_cast<const __half*>(p)[i]);
+}
+
 __global__ void ddim_step_kernel(DdimStepParams p) {
     GRID_STRIDE(i, p.n) {
         const int ch = static_cast<int>((i / p.chan_stride) % p.C);
-        const float c = __half2float(p.eps_c[i]);
+        const float c = load_eps(p.eps_c, i, p.eps_is_f32);
         float e = c;
-        if (p.eps_u != nullptr && ch < p.guided_channels) e = cfg_combine(c, __half2float(p.eps_u[i]), p.g, p.cfg_fp16);
+        if (p.eps_u != nullptr && ch < p.guided_channels) e = cfg_combine(c, load_eps(p.eps_u, i, p.eps_is_f32), p.g, p.cfg_fp16);
         const float x = p.x[i];
         const float nz = (p.noise != nullptr && p.a4 != 0.f) ? __fmul_rn(p.a4, p.noise[i]) : 0.f;
         float xn;
@@ -300,11 +304,11 @@ __global__ void lincomb_kernel(float* out, LincombArgs a, long long n) {
     }
 }
 
-__global__ void cfg_x0_kernel(const float* x, const __half* ec, const __half* eu, float* x0, long long n, float g,
+__global__ void cfg_x0_kernel(const float* x, const void* ec, const void* eu, int eps_f32, float* x0, long long n, float g,
                               float alpha, float sigma, int fp16) {
     GRID_STRIDE(i, n) {
-        float e = __half2float(ec[i]);
-        if (eu != nullptr) e = cfg_combine(e, __half2float(eu[i]), g, fp16);
+        float e = load_eps(ec, i, eps_f32);
+        if (eu != nullptr) e = cfg_combine(e, load_eps(eu, i, eps_f32), g, fp16);
         x0[i] = __fdiv_rn(__fsub_rn(x[i], __fmul_rn(sigma, e)), alpha);
     }
 }
@@ -404,9 +408,9 @@ int lincomb(float* out, const float* const* src, const float* coef, int n_src, l
     lincomb_kernel<<<grid_for(n, 256), 256, 0, stream>>>(out, a, n);
     return ok();
 }
-int cfg_x0(const float* x, const __half* eps_c, const __half* eps_u, float* x0, long long n, float g, float alpha,
-           float sigma, int cfg_fp16, cudaStream_t stream) {
-    cfg_x0_kernel<<<grid_for(n, 256), 256, 0, stream>>>(x, eps_c, eps_u, x0, n, g, alpha, sigma, cfg_fp16);
+int cfg_x0(const float* x, const void* eps_c, const void* eps_u, int eps_is_f32, float* x0, long long n, float g,
+           float alpha, float sigma, int cfg_fp16, cudaStream_t stream) {
+    cfg_x0_kernel<<<grid_for(n, 256), 256, 0, stream>>>(x, eps_c, eps_u, eps_is_f32, x0, n, g, alpha, sigma, cfg_fp16);
     return ok();
 }
 

@@ -447,8 +447,8 @@ int gemm_plan(const GemmProblem& p, GemmPlan* plan, int num_sms) {
         const int nb = p.b_batch_dim >= 0 ? g.dim[p.b_batch_dim] : p.ntaps;
         cuuint64_t dims[3] = {static_cast<cuuint64_t>(p.K), static_cast<cuuint64_t>(p.n_alloc),
                               static_cast<cuuint64_t>(nb)};
-        cuuint64_t strides[2] = {static_cast<cuuint64_t>(p.K) * 2,
-                                 static_cast<cuuint64_t>(p.K) * 2 * static_cast<cuuint64_t>(p.n_alloc)};
+        const cuuint64_t ldb = static_cast<cuuint64_t>(p.ldb > 0 ? p.ldb : p.K);
+        cuuint64_t strides[2] = {ldb * 2, ldb * 2 * static_cast<cuuint64_t>(p.n_alloc)};
         cuuint32_t box[3] = {GEMM_BLOCK_K, static_cast<cuuint32_t>(bn), 1};
         if (encode_map(&g.map_b, p.b, 3, dims, strides, box) != 0) return -6;
     }

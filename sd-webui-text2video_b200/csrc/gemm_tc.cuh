@@ -58,6 +58,7 @@ struct GemmProblem {
     int ntaps;
     int tap_off[GEMM_MAX_TAPS][GEMM_MAX_RDIMS];
     const __half* b;                 // packed [taps or batch][n_alloc][K]
+    long long ldb;                   // row pitch of b in elements (0 -> K)
     int n_alloc;                     // allocated rows per tap in b (>= N, allows padding for tiny N)
     int N;
     int b_batch_dim;                 // -1 if none

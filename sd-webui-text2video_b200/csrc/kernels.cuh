@@ -70,8 +70,9 @@ int convert_to_f16(const void* src, int src_is_f32, __half* dst, long long n, cu
 // sampler updates (fp32 latents [B,C,F,h,w]; eps from the UNet in fp16, cond / uncond)
 struct DdimStepParams {
     const float* x;           // x_t
-    const __half* eps_c;      // conditional eps
-    const __half* eps_u;      // unconditional eps (null -> no guidance)
+    const void* eps_c;        // conditional eps (fp16, or fp32 when eps_is_f32)
+    const void* eps_u;        // unconditional eps (null -> no guidance)
+    int eps_is_f32;
     float* x_out;             // x_{t-1}
     long long n;              // elements
     long long chan_stride;    // F*h*w  (elements per channel)
@@ -90,7 +91,7 @@ int ddim_step(const DdimStepParams& p, cudaStream_t stream);
 // out = sum_i coef[i] * src[i]  (fp32), n_src <= 8  -- UniPC predictor/corrector combinations
 int lincomb(float* out, const float* const* src, const float* coef, int n_src, long long n, cudaStream_t stream);
 // CFG combine for UniPC: eps = u + g (c - u) in fp16 rounding, then x0 = (x - sigma*eps)/alpha  -> fp32
-int cfg_x0(const float* x, const __half* eps_c, const __half* eps_u, float* x0, long long n, float g, float alpha,
-           float sigma, int cfg_fp16, cudaStream_t stream);
+int cfg_x0(const float* x, const void* eps_c, const void* eps_u, int eps_is_f32, float* x0, long long n, float g,
+           float alpha, float sigma, int cfg_fp16, cudaStream_t stream);
 
 }  // namespace t2v

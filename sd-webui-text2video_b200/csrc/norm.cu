@@ -13,6 +13,7 @@ namespace {
 
 constexpr int kGroups = 32;
 constexpr int kStatsThreads = 256;   // 32 vector lanes (x) x 8 row lanes (y)
+constexpr size_t kCounterBytes = 1 << 20;   // up to 262144 norm instances (frames x samples) per call
 
 // partial[(inst * nchunks + chunk) * 32 + g] = (sum, sumsq) ; the last block of an instance folds them (in
 // chunk order, double precision) into stats[inst*32+g] = (mean, rstd) -> deterministic, no float atomics in HBM.
@@ -30,34 +31,52 @@ __global__ void __launch_bounds__(kStatsThreads) gn_stats_kernel(const __half* _
     const int tx = threadIdx.x & 31;
     const int ty = threadIdx.x >> 5;
     const int C8 = C >> 3;
-    for (int i = threadIdx.x; i < 2 * C; i += kStatsThreads) sm[i] = 0.f;
-    __syncthreads();
+    // cross-row-lane reduction through a fixed-order smem tree (no atomics: bit-reproducible run to run)
+    __shared__ float red[8][2][256];       // [row lane][sum|sumsq][32 vectors x 8 channels of the current pass]
     const int r0 = chunk * rows_per_chunk;
     const int r1 = min(r0 + rows_per_chunk, rows_per_inst);
     const __half* base = x + static_cast<long long>(inst) * rows_per_inst * ld;
-    for (int vc = tx; vc < C8; vc += 32) {
+    for (int v0 = 0; v0 < C8; v0 += 32) {          // uniform trip count: barriers inside are safe
+        const int vc = v0 + tx;
         float s[8], q[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) s[e] = q[e] = 0.f;
-        for (int r = r0 + ty; r < r1; r += 8) {
-            const uint4 v = __ldg(reinterpret_cast<const uint4*>(base + r * ld + vc * 8));
-            const __half2* h2 = reinterpret_cast<const __half2*>(&v);
+        if (vc < C8) {
+            for (int r = r0 + ty; r < r1; r += 8) {
+                const uint4 v = __ldg(reinterpret_cast<const uint4*>(base + r * ld + vc * 8));
+                const __half2* h2 = reinterpret_cast<const __half2*>(&v);
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const float2 f = __half22float2(h2[e]);
-                s[2 * e] += f.x;
-                q[2 * e] += f.x * f.x;
-                s[2 * e + 1] += f.y;
-                q[2 * e + 1] += f.y * f.y;
+                for (int e = 0; e < 4; ++e) {
+                    const float2 f = __half22float2(h2[e]);
+                    s[2 * e] += f.x;
+                    q[2 * e] += f.x * f.x;
+                    s[2 * e + 1] += f.y;
+                    q[2 * e + 1] += f.y * f.y;
+                }
             }
         }
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-            atomicAdd(&s_sum[vc * 8 + e], s[e]);
-            atomicAdd(&s_sq[vc * 8 + e], q[e]);
+            red[ty][0][tx * 8 + e] = s[e];
+            red[ty][1][tx * 8 + e] = q[e];
         }
+        __syncthreads();
+        {
+            const int ch = threadIdx.x;                 // 256 threads <-> 256 channels of this pass
+            const int gc = v0 * 8 + ch;
+            if (gc < C) {
+                float a = 0.f, b = 0.f;
+#pragma unroll
+                for (int y = 0; y < 8; ++y) {
+                    a += red[y][0][ch];
+                    b += red[y][1][ch];
+                }
+                s_sum[gc] = a;
+                s_sq[gc] = b;
+            }
+        }
+        __syncthreads();
     }
-    __syncthreads();
     const int cpg = C / kGroups;
     if (threadIdx.x < kGroups) {
         float a = 0.f, b = 0.f;
@@ -79,7 +98,7 @@ __global__ void __launch_bounds__(kStatsThreads) gn_stats_kernel(const __half* _
         if (threadIdx.x < kGroups) {
             double a = 0.0, b = 0.0;
             for (int ch = 0; ch < nchunks; ++ch) {
-                const float2 p = partial[(static_cast<long long>(inst) * nchunks + ch) * kGroups + threadIdx.x];
+                const float2 p = __ldcg(&partial[(static_cast<long long>(inst) * nchunks + ch) * kGroups + threadIdx.x]);
                 a += p.x;
                 b += p.y;
             }
@@ -208,9 +227,10 @@ int gn_rows_per_chunk(int rows_per_inst, int n_inst, int num_sms) {
 size_t gn_workspace_bytes(int rows_per_inst, int n_inst, int num_sms) {
     const int rpc = gn_rows_per_chunk(rows_per_inst, n_inst, num_sms);
     const int nchunks = (rows_per_inst + rpc - 1) / rpc;
-    // partials + stats + counters
-    return static_cast<size_t>(n_inst) * nchunks * kGroups * sizeof(float2) + static_cast<size_t>(n_inst) * kGroups * sizeof(float2) +
-           static_cast<size_t>(n_inst) * sizeof(unsigned int) + 256;
+    // counters (fixed-size region at the START: their location must not depend on the call's shape, they have to
+    // stay zero between launches) + stats + partials
+    return kCounterBytes + static_cast<size_t>(n_inst) * kGroups * sizeof(float2) +
+           static_cast<size_t>(n_inst) * nchunks * kGroups * sizeof(float2) + 256;
 }
 
 int groupnorm_silu(const __half* x, long long ldx, __half* y, long long ldy, long long rows, int C, int rows_per_inst,
@@ -220,10 +240,11 @@ int groupnorm_silu(const __half* x, long long ldx, __half* y, long long ldy, lon
     const int n_inst = static_cast<int>(rows / rows_per_inst);
     const int rpc = gn_rows_per_chunk(rows_per_inst, n_inst, num_sms);
     const int nchunks = (rows_per_inst + rpc - 1) / rpc;
+    if (static_cast<size_t>(n_inst) * sizeof(unsigned int) > kCounterBytes) return -3;
     uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
-    float2* partial = reinterpret_cast<float2*>(ws);
-    float2* stats = partial + static_cast<size_t>(n_inst) * nchunks * kGroups;
-    unsigned int* counters = reinterpret_cast<unsigned int*>(stats + static_cast<size_t>(n_inst) * kGroups);
+    unsigned int* counters = reinterpret_cast<unsigned int*>(ws);
+    float2* stats = reinterpret_cast<float2*>(ws + kCounterBytes);
+    float2* partial = stats + static_cast<size_t>(n_inst) * kGroups;
     gn_stats_kernel<<<dim3(nchunks, n_inst), kStatsThreads, 2 * C * sizeof(float), stream>>>(
         x, ldx, C, rows_per_inst, rpc, nchunks, eps, partial, counters, stats);
     const long long total = rows * (C / 8);

@@ -2,6 +2,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 namespace t2v {
@@ -49,6 +50,7 @@ int ParamStore::set(const std::string& name, const void* src, int dtype, int ndi
             set_error("cudaMalloc failed for parameter '%s'", name.c_str());
             return -4;
         }
+        cudaMemsetAsync(p.data, 0, ((p.elems + 7) / 8 * 8) * sizeof(__half), s);   // zero tail: padded bias reads
     }
     int rc = convert_to_f16(src, dtype, p.data, p.elems, s);
     if (rc != 0) return rc;
@@ -66,6 +68,22 @@ int ParamStore::missing(std::string* one) const {
             ++n;
         }
     return n;
+}
+
+int ParamStore::info(int index, std::string* name, std::vector<long long>* shape) const {
+    int i = 0, n = 0;
+    bool found = false;
+    for (auto& kv : params_) {
+        if (!kv.second.expected) continue;
+        if (i == index) {
+            *name = kv.first;
+            *shape = kv.second.shape;
+            found = true;
+        }
+        ++i;
+        ++n;
+    }
+    return found ? n : -1;
 }
 
 const Param& ParamStore::get(const std::string& name) const {
@@ -222,5 +240,199 @@ void taps_temporal(GemmProblem& p) {
         p.tap_off[kt][3] = 0;
     }
 }
+
+
+// ----------------------------------------------------------------------------------------- shared layer helpers
+int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+// packed weights -------------------------------------------------------------------------------------------
+// conv / linear weight [Cout, Cin, taps...] -> [taps][n_alloc][k_alloc]
+const __half* w_conv(NetCtx& c, const std::string& name, int taps, int n_alloc, int k_alloc) {
+    if (c.b->dry()) return nullptr;     // shape-only pass (flop / memory model): no parameters needed
+    ParamStore& P = *c.params;
+    const Param& prm = P.get(name);
+    if (!prm.data) {
+        c.b->error = -10;
+        return nullptr;
+    }
+    const int cout = static_cast<int>(prm.shape[0]), cin = static_cast<int>(prm.shape[1]);
+    if (n_alloc == 0) n_alloc = cout;
+    if (k_alloc == 0) k_alloc = cin;
+    if (taps == 1 && n_alloc == cout && k_alloc == cin) return prm.data;     // already [N][K]
+    const std::string key = name + "#t" + std::to_string(taps) + "n" + std::to_string(n_alloc) + "k" + std::to_string(k_alloc);
+    if (__half* p = P.packed(key)) return p;
+    if (c.b->dry()) return nullptr;
+    __half* dst = P.new_packed(key, static_cast<long long>(taps) * n_alloc * k_alloc);
+    if (!dst || pack_conv_weight(prm.data, 0, dst, cout, cin, taps, n_alloc, k_alloc, c.stream) != 0) c.b->error = -11;
+    return dst;
+}
+// stride-2 conv weight [Cout, Cin, 3, 3] -> [1][Cout][9*Cin] with K index = tap*Cin + c (matches im2col_s2 columns)
+const __half* w_conv_kmajor(NetCtx& c, const std::string& name) {
+    if (c.b->dry()) return nullptr;
+    ParamStore& P = *c.params;
+    const Param& prm = P.get(name);
+    if (!prm.data) {
+        c.b->error = -10;
+        return nullptr;
+    }
+    const int cout = static_cast<int>(prm.shape[0]), cin = static_cast<int>(prm.shape[1]);
+    const std::string key = name + "#kmajor";
+    if (__half* p = P.packed(key)) return p;
+    if (c.b->dry()) return nullptr;
+    // [9][Cout][Cin] first, then view-transpose by a second pack: treat as conv weight with "Cin" = 9*Cin, taps = 1
+    // pack_conv_weight source index = (o*Cin + k)*taps + tap ; we want dst[o][tap*Cin + k] -> do it tap by tap
+    __half* dst = P.new_packed(key, static_cast<long long>(cout) * 9 * cin);
+    __half* tmp = P.new_packed(key + "#tmp", static_cast<long long>(9) * cout * cin);
+    if (!dst || !tmp || pack_conv_weight(prm.data, 0, tmp, cout, cin, 9, cout, cin, c.stream) != 0) {
+        c.b->error = -11;
+        return dst;
+    }
+    for (int tap = 0; tap < 9; ++tap)
+        cudaMemcpy2DAsync(dst + static_cast<long long>(tap) * cin, static_cast<size_t>(9) * cin * 2,
+                          tmp + static_cast<long long>(tap) * cout * cin, static_cast<size_t>(cin) * 2,
+                          static_cast<size_t>(cin) * 2, cout, cudaMemcpyDeviceToDevice, c.stream);
+    return dst;
+}
+// concatenated bias-free projections (q|k|v or k|v) -> one [sum N, K] matrix
+const __half* w_cat(NetCtx& c, const std::vector<std::string>& names) {
+    if (c.b->dry()) return nullptr;
+    ParamStore& P = *c.params;
+    std::string key = "cat";
+    long long total = 0;
+    for (auto& n : names) {
+        key += "#" + n;
+        const Param& prm = P.get(n);
+        if (!prm.data) {
+            c.b->error = -10;
+            return nullptr;
+        }
+        total += prm.elems;
+    }
+    if (__half* p = P.packed(key)) return p;
+    if (c.b->dry()) return nullptr;
+    __half* dst = P.new_packed(key, total);
+    if (!dst) {
+        c.b->error = -11;
+        return nullptr;
+    }
+    long long off = 0;
+    for (auto& n : names) {
+        const Param& prm = P.get(n);
+        cudaMemcpyAsync(dst + off, prm.data, prm.elems * sizeof(__half), cudaMemcpyDeviceToDevice, c.stream);
+        off += prm.elems;
+    }
+    return dst;
+}
+Geglu w_geglu(NetCtx& c, const std::string& prefix, int H, int K, int bn) {
+    if (c.b->dry()) return Geglu{nullptr, nullptr, bn};
+    ParamStore& P = *c.params;
+    const Param& w = P.get(prefix + ".weight");
+    const Param& bb = P.get(prefix + ".bias");
+    Geglu g{nullptr, nullptr, bn};
+    if (!w.data || !bb.data) {
+        c.b->error = -10;
+        return g;
+    }
+    const std::string key = prefix + "#geglu" + std::to_string(bn);
+    if (__half* p = P.packed(key)) {
+        g.w = p;
+        g.b = P.packed(key + "#b");
+        return g;
+    }
+    if (c.b->dry()) return g;
+    __half* wd = P.new_packed(key, static_cast<long long>(2) * H * K);
+    __half* bd = P.new_packed(key + "#b", static_cast<long long>(2) * H);
+    if (!wd || !bd || pack_geglu_weight(w.data, bb.data, 0, wd, bd, H, K, bn, c.stream) != 0) c.b->error = -11;
+    g.w = wd;
+    g.b = bd;
+    return g;
+}
+const __half* prm(NetCtx& c, const std::string& name) {
+    if (c.b->dry()) return nullptr;
+    const Param& p = (*c.params).get(name);
+    if (!p.data) c.b->error = -10;
+    return p.data;
+}
+
+// elementary ops -----------------------------------------------------------------------------------------------
+GemmProblem base_problem(const Tok& a, int K, const __half* w, int n_alloc, int N, const Tok& out) {
+    GemmProblem p;
+    memset(&p, 0, sizeof(p));
+    p.a = a.p;
+    p.lda = a.ld;
+    p.K = K;
+    p.nd = 1;
+    p.dim[0] = static_cast<int>(a.rows);
+    p.ntaps = 1;
+    p.b = w;
+    p.n_alloc = n_alloc;
+    p.N = N;
+    p.b_batch_dim = -1;
+    p.out = out.p;
+    p.ldo = out.ld;
+    p.alpha = 1.0f;
+    return p;
+}
+
+// y = x W^T (+bias) (+residual)
+Tok linear(NetCtx& c, const Tok& x, const __half* w, int N, const __half* bias, const Tok* residual, int K) {
+    Tok y = c.b->alloc(x.rows, N);
+    GemmProblem p = base_problem(x, K ? K : x.C, w, N, N, y);
+    p.bias = bias;
+    if (residual) {
+        p.residual = residual->p;
+        p.ldr = residual->ld;
+    }
+    c.b->gemm(p);
+    return y;
+}
+
+Tok group_norm(NetCtx& c, const Tok& x, const std::string& prefix, long long rows_per_inst, float eps, bool silu) {
+    Tok y = c.b->alloc(x.rows, x.C);
+    const __half* g = prm(c, prefix + ".weight");
+    const __half* bt = prm(c, prefix + ".bias");
+    void* ws = c.gn_ws;
+    const int sms = c.b->sms();
+    const Tok xx = x;
+    c.b->step([=](cudaStream_t s) {
+        return groupnorm_silu(xx.p, xx.ld, y.p, y.ld, xx.rows, xx.C, static_cast<int>(rows_per_inst), g, bt, eps, silu ? 1 : 0,
+                              ws, sms, s);
+    }, 2);
+    return y;
+}
+
+Tok layer_norm(NetCtx& c, const Tok& x, const std::string& prefix) {
+    Tok y = c.b->alloc(x.rows, x.C);
+    const __half* g = prm(c, prefix + ".weight");
+    const __half* bt = prm(c, prefix + ".bias");
+    const Tok xx = x;
+    c.b->step([=](cudaStream_t s) { return layernorm(xx.p, xx.ld, y.p, y.ld, xx.rows, xx.C, g, bt, 1e-5f, s); });
+    return y;
+}
+
+
+Tok conv3x3(NetCtx& c, const Tok& x, const std::string& wname, const __half* bias, int bias_rows, long long bias_stride,
+            int N, int hcur, int wcur, const Tok* residual, int n_alloc) {
+    const int frames = static_cast<int>(x.rows / (static_cast<long long>(hcur) * wcur));
+    const int k_alloc = x.C;       // activations may carry zero-padded channels (stem): weights padded to match
+    const __half* w = w_conv(c, wname, 9, n_alloc ? n_alloc : N, k_alloc);
+    Tok y = c.b->alloc(x.rows, N, N % 8 == 0 ? N : round_up(N, 8));
+    GemmProblem p = base_problem(x, x.C, w, n_alloc ? n_alloc : N, N, y);
+    p.nd = 3;
+    p.dim[0] = wcur;
+    p.dim[1] = hcur;
+    p.dim[2] = frames;
+    taps_3x3(p);
+    p.bias = bias;
+    p.bias_rows = bias_rows;
+    p.bias_stride = bias_stride;
+    if (residual) {
+        p.residual = residual->p;
+        p.ldr = residual->ld;
+    }
+    c.b->gemm(p);
+    return y;
+}
+
 
 }  // namespace t2v

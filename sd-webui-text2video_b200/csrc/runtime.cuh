@@ -31,6 +31,7 @@ public:
     void expect(const std::string& name, std::vector<long long> shape);
     int set(const std::string& name, const void* src, int dtype, int ndim, const int64_t* shape, cudaStream_t s);
     int missing(std::string* one) const;
+    int info(int index, std::string* name, std::vector<long long>* shape) const;   // returns count, -1 if out of range
     const Param& get(const std::string& name) const;     // aborts via set_error + null data if absent
     bool has(const std::string& name) const { return params_.count(name) != 0; }
     // packed variants, created lazily and cached until any parameter changes
@@ -107,6 +108,29 @@ private:
     bool dry_;
     int sms_;
 };
+
+// ----------------------------------------------------------------------------------------- layer helpers
+struct NetCtx {
+    ParamStore* params;
+    Builder* b;
+    cudaStream_t stream;      // weight-packing kernels are enqueued here while the plan is built
+    void* gn_ws;              // zero-initialised groupnorm workspace (partials, stats, counters)
+};
+int round_up(int v, int m);
+// packed-weight accessors (created on first use, cached in the ParamStore until a parameter changes)
+const __half* w_conv(NetCtx& c, const std::string& name, int taps, int n_alloc = 0, int k_alloc = 0);
+const __half* w_conv_kmajor(NetCtx& c, const std::string& name);
+const __half* w_cat(NetCtx& c, const std::vector<std::string>& names);
+struct Geglu { const __half* w; const __half* b; int bn; };
+Geglu w_geglu(NetCtx& c, const std::string& prefix, int H, int K, int bn);
+const __half* prm(NetCtx& c, const std::string& name);
+// recorded ops
+GemmProblem base_problem(const Tok& a, int K, const __half* w, int n_alloc, int N, const Tok& out);
+Tok linear(NetCtx& c, const Tok& x, const __half* w, int N, const __half* bias, const Tok* residual, int K = 0);
+Tok group_norm(NetCtx& c, const Tok& x, const std::string& prefix, long long rows_per_inst, float eps, bool silu);
+Tok layer_norm(NetCtx& c, const Tok& x, const std::string& prefix);
+Tok conv3x3(NetCtx& c, const Tok& x, const std::string& wname, const __half* bias, int bias_rows, long long bias_stride,
+            int N, int hcur, int wcur, const Tok* residual, int n_alloc = 0);
 
 // conv taps helpers over row dims (w, h, frames) and (pixels, frames, samples)
 void taps_3x3(GemmProblem& p);

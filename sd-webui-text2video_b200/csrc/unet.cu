@@ -215,179 +215,13 @@ void expect_params(t2v_unet* u) {
 }
 
 // ------------------------------------------------------------------------------------------ plan construction
-struct Ctx {
+struct Ctx : NetCtx {
     t2v_unet* u;
-    Builder* b;
-    cudaStream_t stream;      // packing kernels run here while the plan is built
     int B, F, h, w, L;
-    void* gn_ws;
     __half* emb;              // [B, E] time embedding (after time_embed MLP)
     __half* ctx;              // [B*L, ctx_dim] fixed staging of the text conditioning
     Plan* plan;
 };
-
-inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
-
-// packed weights -------------------------------------------------------------------------------------------
-// conv / linear weight [Cout, Cin, taps...] -> [taps][n_alloc][k_alloc]
-const __half* w_conv(Ctx& c, const std::string& name, int taps, int n_alloc = 0, int k_alloc = 0) {
-    ParamStore& P = c.u->params;
-    const Param& prm = P.get(name);
-    if (!prm.data) {
-        c.b->error = -10;
-        return nullptr;
-    }
-    const int cout = static_cast<int>(prm.shape[0]), cin = static_cast<int>(prm.shape[1]);
-    if (n_alloc == 0) n_alloc = cout;
-    if (k_alloc == 0) k_alloc = cin;
-    if (taps == 1 && n_alloc == cout && k_alloc == cin) return prm.data;     // already [N][K]
-    const std::string key = name + "#t" + std::to_string(taps) + "n" + std::to_string(n_alloc) + "k" + std::to_string(k_alloc);
-    if (__half* p = P.packed(key)) return p;
-    if (c.b->dry()) return nullptr;
-    __half* dst = P.new_packed(key, static_cast<long long>(taps) * n_alloc * k_alloc);
-    if (!dst || pack_conv_weight(prm.data, 0, dst, cout, cin, taps, n_alloc, k_alloc, c.stream) != 0) c.b->error = -11;
-    return dst;
-}
-// stride-2 conv weight [Cout, Cin, 3, 3] -> [1][Cout][9*Cin] with K index = tap*Cin + c (matches im2col_s2 columns)
-const __half* w_conv_kmajor(Ctx& c, const std::string& name) {
-    ParamStore& P = c.u->params;
-    const Param& prm = P.get(name);
-    if (!prm.data) {
-        c.b->error = -10;
-        return nullptr;
-    }
-    const int cout = static_cast<int>(prm.shape[0]), cin = static_cast<int>(prm.shape[1]);
-    const std::string key = name + "#kmajor";
-    if (__half* p = P.packed(key)) return p;
-    if (c.b->dry()) return nullptr;
-    // [9][Cout][Cin] first, then view-transpose by a second pack: treat as conv weight with "Cin" = 9*Cin, taps = 1
-    // pack_conv_weight source index = (o*Cin + k)*taps + tap ; we want dst[o][tap*Cin + k] -> do it tap by tap
-    __half* dst = P.new_packed(key, static_cast<long long>(cout) * 9 * cin);
-    __half* tmp = P.new_packed(key + "#tmp", static_cast<long long>(9) * cout * cin);
-    if (!dst || !tmp || pack_conv_weight(prm.data, 0, tmp, cout, cin, 9, cout, cin, c.stream) != 0) {
-        c.b->error = -11;
-        return dst;
-    }
-    for (int tap = 0; tap < 9; ++tap)
-        cudaMemcpy2DAsync(dst + static_cast<long long>(tap) * cin, static_cast<size_t>(9) * cin * 2,
-                          tmp + static_cast<long long>(tap) * cout * cin, static_cast<size_t>(cin) * 2,
-                          static_cast<size_t>(cin) * 2, cout, cudaMemcpyDeviceToDevice, c.stream);
-    return dst;
-}
-// concatenated bias-free projections (q|k|v or k|v) -> one [sum N, K] matrix
-const __half* w_cat(Ctx& c, const std::vector<std::string>& names) {
-    ParamStore& P = c.u->params;
-    std::string key = "cat";
-    long long total = 0;
-    for (auto& n : names) {
-        key += "#" + n;
-        const Param& prm = P.get(n);
-        if (!prm.data) {
-            c.b->error = -10;
-            return nullptr;
-        }
-        total += prm.elems;
-    }
-    if (__half* p = P.packed(key)) return p;
-    if (c.b->dry()) return nullptr;
-    __half* dst = P.new_packed(key, total);
-    if (!dst) {
-        c.b->error = -11;
-        return nullptr;
-    }
-    long long off = 0;
-    for (auto& n : names) {
-        const Param& prm = P.get(n);
-        cudaMemcpyAsync(dst + off, prm.data, prm.elems * sizeof(__half), cudaMemcpyDeviceToDevice, c.stream);
-        off += prm.elems;
-    }
-    return dst;
-}
-struct Geglu { const __half* w; const __half* b; int bn; };
-Geglu w_geglu(Ctx& c, const std::string& prefix, int H, int K, int bn) {
-    ParamStore& P = c.u->params;
-    const Param& w = P.get(prefix + ".weight");
-    const Param& bb = P.get(prefix + ".bias");
-    Geglu g{nullptr, nullptr, bn};
-    if (!w.data || !bb.data) {
-        c.b->error = -10;
-        return g;
-    }
-    const std::string key = prefix + "#geglu" + std::to_string(bn);
-    if (__half* p = P.packed(key)) {
-        g.w = p;
-        g.b = P.packed(key + "#b");
-        return g;
-    }
-    if (c.b->dry()) return g;
-    __half* wd = P.new_packed(key, static_cast<long long>(2) * H * K);
-    __half* bd = P.new_packed(key + "#b", static_cast<long long>(2) * H);
-    if (!wd || !bd || pack_geglu_weight(w.data, bb.data, 0, wd, bd, H, K, bn, c.stream) != 0) c.b->error = -11;
-    g.w = wd;
-    g.b = bd;
-    return g;
-}
-const __half* prm(Ctx& c, const std::string& name) {
-    const Param& p = c.u->params.get(name);
-    if (!p.data) c.b->error = -10;
-    return p.data;
-}
-
-// elementary ops -----------------------------------------------------------------------------------------------
-GemmProblem base_problem(const Tok& a, int K, const __half* w, int n_alloc, int N, const Tok& out) {
-    GemmProblem p;
-    memset(&p, 0, sizeof(p));
-    p.a = a.p;
-    p.lda = a.ld;
-    p.K = K;
-    p.nd = 1;
-    p.dim[0] = static_cast<int>(a.rows);
-    p.ntaps = 1;
-    p.b = w;
-    p.n_alloc = n_alloc;
-    p.N = N;
-    p.b_batch_dim = -1;
-    p.out = out.p;
-    p.ldo = out.ld;
-    p.alpha = 1.0f;
-    return p;
-}
-
-// y = x W^T (+bias) (+residual)
-Tok linear(Ctx& c, const Tok& x, const __half* w, int N, const __half* bias, const Tok* residual, int K = 0) {
-    Tok y = c.b->alloc(x.rows, N);
-    GemmProblem p = base_problem(x, K ? K : x.C, w, N, N, y);
-    p.bias = bias;
-    if (residual) {
-        p.residual = residual->p;
-        p.ldr = residual->ld;
-    }
-    c.b->gemm(p);
-    return y;
-}
-
-Tok group_norm(Ctx& c, const Tok& x, const std::string& prefix, long long rows_per_inst, float eps, bool silu) {
-    Tok y = c.b->alloc(x.rows, x.C);
-    const __half* g = prm(c, prefix + ".weight");
-    const __half* bt = prm(c, prefix + ".bias");
-    void* ws = c.gn_ws;
-    const int sms = c.b->sms();
-    const Tok xx = x;
-    c.b->step([=](cudaStream_t s) {
-        return groupnorm_silu(xx.p, xx.ld, y.p, y.ld, xx.rows, xx.C, static_cast<int>(rows_per_inst), g, bt, eps, silu ? 1 : 0,
-                              ws, sms, s);
-    }, 2);
-    return y;
-}
-
-Tok layer_norm(Ctx& c, const Tok& x, const std::string& prefix) {
-    Tok y = c.b->alloc(x.rows, x.C);
-    const __half* g = prm(c, prefix + ".weight");
-    const __half* bt = prm(c, prefix + ".bias");
-    const Tok xx = x;
-    c.b->step([=](cudaStream_t s) { return layernorm(xx.p, xx.ld, y.p, y.ld, xx.rows, xx.C, g, bt, 1e-5f, s); });
-    return y;
-}
 
 void tap(Ctx& c, const std::string& name, const Tok& t, int h, int w) {
     if (c.u->taps_enabled && !c.b->dry()) c.plan->taps[name] = {t, {h, w}};
@@ -440,7 +274,7 @@ Tok transformer_block(Ctx& c, Tok x, const std::string& p, int heads, int hcur, 
                 ap_.o_ss = P * o.ld;
             }
         } else {
-            const Param& wk = c.u->params.get(ap + ".to_k.weight");
+            const Param& wk = c.params->get(ap + ".to_k.weight");
             const int ctx_dim = wk.data ? static_cast<int>(wk.shape[1]) : c.u->cfg.context_dim;
             qkv = linear(c, l, prm(c, ap + ".to_q.weight"), C, nullptr, nullptr);
             // K/V of the prompt: identical for every frame (the reference recomputes them per frame, :426,:545-546)
@@ -473,7 +307,7 @@ Tok transformer_block(Ctx& c, Tok x, const std::string& p, int heads, int hcur, 
             c.b->add_flops(4.0 * apc.batch * apc.heads * static_cast<double>(apc.sq) * apc.skv * 64);
         }
         c.b->free(qkv);
-        if (kv.p || (!self_attn)) c.b->free(kv);
+        if (!self_attn) c.b->free(kv);
         Tok y = linear(c, o, prm(c, ap + ".to_out.0.weight"), C, prm(c, ap + ".to_out.0.bias"), &x);
         c.b->free(o);
         c.b->free(x);
@@ -509,29 +343,6 @@ Tok transformer(Ctx& c, const Tok& x, const Blk& blk, int hcur, int wcur, bool t
     Tok h3 = transformer_block(c, h0, p + ".transformer_blocks.0", blk.heads, hcur, wcur, temporal);
     Tok y = linear(c, h3, prm(c, p + ".proj_out.weight"), blk.cin, prm(c, p + ".proj_out.bias"), &x);
     c.b->free(h3);
-    return y;
-}
-
-Tok conv3x3(Ctx& c, const Tok& x, const std::string& wname, const __half* bias, int bias_rows, long long bias_stride,
-            int N, int hcur, int wcur, const Tok* residual, int n_alloc = 0) {
-    const int frames = static_cast<int>(x.rows / (static_cast<long long>(hcur) * wcur));
-    const int k_alloc = x.C;       // activations may carry zero-padded channels (stem): weights padded to match
-    const __half* w = w_conv(c, wname, 9, n_alloc ? n_alloc : N, k_alloc);
-    Tok y = c.b->alloc(x.rows, N, N % 8 == 0 ? N : round_up(N, 8));
-    GemmProblem p = base_problem(x, x.C, w, n_alloc ? n_alloc : N, N, y);
-    p.nd = 3;
-    p.dim[0] = wcur;
-    p.dim[1] = hcur;
-    p.dim[2] = frames;
-    taps_3x3(p);
-    p.bias = bias;
-    p.bias_rows = bias_rows;
-    p.bias_stride = bias_stride;
-    if (residual) {
-        p.residual = residual->p;
-        p.ldr = residual->ld;
-    }
-    c.b->gemm(p);
     return y;
 }
 
@@ -623,13 +434,21 @@ Tok upsample(Ctx& c, const Tok& x, const Blk& blk, int hcur, int wcur) {
 struct IO {
     __half* x_tok;      // [R, 8]
     float* t;           // [B]
+    __half* ctx;        // [B*L, context_dim]
     __half* out_tok;    // [R, 8]
 };
 
 int build(t2v_unet* u, Plan* plan, Arena* arena, bool dry, cudaStream_t stream, int B, int F, int h, int w, int L,
           IO* io) {
     Builder bld(plan, arena, dry, num_sms());
-    Ctx c{u, &bld, stream, B, F, h, w, L, u->gn_ws, nullptr, nullptr, plan};
+    Ctx c;
+    c.params = &u->params;
+    c.b = &bld;
+    c.stream = stream;
+    c.gn_ws = u->gn_ws;
+    c.u = u;
+    c.B = B; c.F = F; c.h = h; c.w = w; c.L = L;
+    c.emb = nullptr; c.ctx = nullptr; c.plan = plan;
     const t2v_unet_config& cfg = u->cfg;
     const int E = cfg.dim * 4;
     const long long R0 = static_cast<long long>(B) * F * h * w;
@@ -641,6 +460,7 @@ int build(t2v_unet* u, Plan* plan, Arena* arena, bool dry, cudaStream_t stream, 
     io->t = reinterpret_cast<float*>(bld.alloc_bytes(static_cast<size_t>(B) * sizeof(float)));
     Tok ctx_tok = bld.alloc(static_cast<long long>(B) * L, cfg.context_dim);
     c.ctx = ctx_tok.p;
+    io->ctx = ctx_tok.p;
     // time embedding: sinusoid -> Linear -> SiLU -> Linear (t2v_model.py:154-156, :420)
     __half* sinus = reinterpret_cast<__half*>(bld.alloc_bytes(static_cast<size_t>(B) * cfg.dim * sizeof(__half)));
     __half* e1 = reinterpret_cast<__half*>(bld.alloc_bytes(static_cast<size_t>(B) * E * sizeof(__half)));
@@ -730,9 +550,6 @@ int build(t2v_unet* u, Plan* plan, Arena* arena, bool dry, cudaStream_t stream, 
     return bld.error;
 }
 
-struct PlanIO {
-    IO io;
-};
 std::map<Plan*, IO> g_io;
 
 Plan* get_plan(t2v_unet* u, int B, int F, int h, int w, int L, cudaStream_t stream) {
@@ -833,6 +650,21 @@ int t2v_unet_missing_params(t2v_unet* u, char* name_out, size_t name_cap) {
     return n;
 }
 
+int t2v_unet_param_info(t2v_unet* u, int index, char* name_out, size_t name_cap, int64_t* shape_out, int* ndim_out) {
+    std::string name;
+    std::vector<long long> shape;
+    const int n = u->params.info(index, &name, &shape);
+    if (n < 0) return -1;
+    if (name_out && name_cap > 0) {
+        strncpy(name_out, name.c_str(), name_cap - 1);
+        name_out[name_cap - 1] = 0;
+    }
+    if (ndim_out) *ndim_out = static_cast<int>(shape.size());
+    if (shape_out)
+        for (size_t i = 0; i < shape.size() && i < 8; ++i) shape_out[i] = shape[i];
+    return n;
+}
+
 int t2v_unet_forward(t2v_unet* u, const void* x, int x_is_f32, const float* t, const void* ctx, void* out,
                      int out_is_f32, int B, int F, int h, int w, int L, void* stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
@@ -844,13 +676,8 @@ int t2v_unet_forward(t2v_unet* u, const void* x, int x_is_f32, const float* t, c
     int rc = ingest_latent(x, x_is_f32, io.x_tok, cin_pad, cin_pad, B, cfg.in_dim, F, h, w, 1.0f, stream);
     if (rc != 0) return rc;
     cudaMemcpyAsync(io.t, t, sizeof(float) * B, cudaMemcpyDeviceToDevice, stream);
-    // ctx staging lives right after t in the slab (allocated third in build())
-    {
-        // recover the ctx staging pointer: it is the Tok allocated after io.t -> recompute as in build()
-        // (stored implicitly: first GEMM on ctx reads it); simpler: keep it next to io
-    }
-    cudaMemcpyAsync(reinterpret_cast<char*>(io.t) + 1024, ctx, static_cast<size_t>(B) * L * cfg.context_dim * sizeof(__half),
-                    cudaMemcpyDeviceToDevice, stream);
+    cudaMemcpyAsync(io.ctx, ctx, static_cast<size_t>(B) * L * cfg.context_dim * sizeof(__half), cudaMemcpyDeviceToDevice,
+                    stream);
     for (auto& s : plan->steps) {
         rc = s(stream);
         if (rc != 0) {

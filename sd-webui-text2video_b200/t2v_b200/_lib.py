@@ -22,6 +22,7 @@ SIGNATURES = {
     't2v_unet_destroy': (None, [P]),
     't2v_unet_set_param': (c_int, [P, c_char_p, P, c_int, c_int, C.POINTER(C.c_int64), P]),
     't2v_unet_missing_params': (c_int, [P, c_char_p, C.c_size_t]),
+    't2v_unet_param_info': (c_int, [P, c_int, c_char_p, C.c_size_t, C.POINTER(C.c_int64), C.POINTER(c_int)]),
     't2v_unet_forward': (c_int, [P, P, c_int, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     't2v_unet_flops': (c_double, [P, c_int, c_int, c_int, c_int, c_int]),
     't2v_unet_num_launches': (c_int, [P]),
@@ -31,11 +32,12 @@ SIGNATURES = {
     't2v_vae_destroy': (None, [P]),
     't2v_vae_set_param': (c_int, [P, c_char_p, P, c_int, c_int, C.POINTER(C.c_int64), P]),
     't2v_vae_missing_params': (c_int, [P, c_char_p, C.c_size_t]),
+    't2v_vae_param_info': (c_int, [P, c_int, c_char_p, C.c_size_t, C.POINTER(C.c_int64), C.POINTER(c_int)]),
     't2v_vae_decode': (c_int, [P, P, c_int, c_float, P, c_int, c_int, c_int, c_int, c_int, P]),
     't2v_vae_flops': (c_double, [P, c_int, c_int, c_int]),
-    't2v_ddim_step': (c_int, [P, P, P, P, c_ll, c_ll, c_int, c_int, c_float, c_int, c_float, c_float, c_float, c_float,
+    't2v_ddim_step': (c_int, [P, P, P, c_int, P, c_ll, c_ll, c_int, c_int, c_float, c_int, c_float, c_float, c_float, c_float,
                               c_float, P, c_int, P]),
-    't2v_cfg_x0': (c_int, [P, P, P, P, c_ll, c_float, c_float, c_float, c_int, P]),
+    't2v_cfg_x0': (c_int, [P, P, P, c_int, P, c_ll, c_float, c_float, c_float, c_int, P]),
     't2v_lincomb': (c_int, [P, C.POINTER(P), C.POINTER(c_float), c_int, c_ll, P]),
     't2v_op_gemm': (c_int, [P, c_ll, c_int, c_int, C.POINTER(c_int), c_int, C.POINTER(c_int), P, c_int, c_int, c_int,
                             c_int, P, c_ll, P, c_int, c_ll, P, c_ll, c_float, c_int, P]),

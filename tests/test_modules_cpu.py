@@ -1,0 +1,84 @@
+"""CPU: the nn.Module mirrors expose the reference's state_dict / module tree (load_state_dict(strict=True), LoRA
+name matching) and schedule buffers -- checked against the oracle's parameter table (itself pinned against the
+reference) and, when mounted, against the reference classes directly."""
+import pytest
+import torch
+import torch.nn as nn
+
+from oracle import unet_oracle as UO, vae_oracle as VO, ref_shim
+from oracle import samplers_oracle as SO
+from t2v_b200.modules import UNetSD, AutoencoderKL
+from t2v_b200.pipeline import VAE_DDCONFIG, linear_sd_betas
+
+
+def test_unet_state_dict_layout_tiny():
+    cfg = UO.UNetConfig(dim=64)
+    net = UNetSD(dim=64)
+    specs = UO.param_specs(cfg)
+    sd = net.state_dict()
+    assert {k: tuple(v.shape) for k, v in sd.items()} == {k: tuple(v) for k, v in specs.items()}
+    net.load_state_dict(UO.make_weights(specs, seed=1), strict=True)
+    with pytest.raises(RuntimeError):
+        bad = dict(UO.make_weights(specs, seed=1))
+        bad['not.a.key'] = torch.zeros(1)
+        net.load_state_dict(bad, strict=True)
+
+
+def test_unet_leaf_types_for_lora_and_typo_key():
+    net = UNetSD(dim=64)
+    mods = dict(net.named_modules())
+    assert isinstance(mods['input_blocks.1.0.in_layers.2'], nn.Conv2d)
+    assert isinstance(mods['input_blocks.1.0.temopral_conv.conv1.2'], nn.Conv3d)          # sic
+    assert isinstance(mods['input_blocks.1.0.temopral_conv.conv2.3'], nn.Conv3d)
+    assert isinstance(mods['input_blocks.1.1.transformer_blocks.0.attn2.to_k'], nn.Linear)
+    assert isinstance(mods['input_blocks.1.2.proj_in'], nn.Conv1d)
+    assert isinstance(mods['input_blocks.1.1.transformer_blocks.0.norm1'], nn.LayerNorm)
+    assert isinstance(mods['input_blocks.1.1.norm'], nn.GroupNorm)
+    assert mods['input_blocks.0.1.proj_in'].weight.shape == (512, 64, 1)                     # stem TT: 8 heads x 64
+    # weights stay re-assignable Parameters (stable_lora/scripts/lora_processor.py:236-242)
+    lin = mods['input_blocks.1.1.transformer_blocks.0.attn2.to_k']
+    lin.weight = nn.Parameter(lin.weight.detach() * 2)
+
+
+def test_vae_state_dict_layout():
+    v = AutoencoderKL(VAE_DDCONFIG, 4)
+    sd = {k: tuple(t.shape) for k, t in v.state_dict().items()}
+    dec = VO.decoder_param_specs(VO.VAEConfig())
+    for k, s in dec.items():
+        assert sd[k] == tuple(s), k
+    assert len(sd) == 248 and 'encoder.conv_in.weight' in sd and 'quant_conv.weight' in sd
+
+
+def test_schedule_buffers_match_oracle():
+    net = UNetSD(dim=64)
+    betas = linear_sd_betas()
+    assert torch.equal(betas, SO.linear_sd_betas())
+    net.register_schedule(given_betas=betas.numpy())
+    acp = torch.cumprod(1 - betas, 0)
+    assert torch.equal(net.alphas_cumprod, acp.to(torch.float32))
+    assert net.num_timesteps == 1000 and net.parameterization == 'eps'
+    assert torch.equal(net.alphas_cumprod_prev[1:], acp[:-1].to(torch.float32)) and net.alphas_cumprod_prev[0] == 1
+
+
+def test_cpu_forward_is_refused():
+    net = UNetSD(dim=64)
+    if torch.cuda.is_available():
+        pytest.skip('GPU present')
+    with pytest.raises(RuntimeError):
+        net(torch.zeros(1, 4, 2, 8, 8), torch.tensor([1]), torch.zeros(1, 77, 1024))
+
+
+@pytest.mark.skipif(not ref_shim.reference_available(), reason='reference tree not mounted')
+def test_mirror_against_reference_classes():
+    m = ref_shim.load_modelscope()
+    ref = m.UNetSD(in_dim=4, dim=64, y_dim=768, context_dim=1024, out_dim=4, dim_mult=[1, 2, 4, 4], num_heads=8,
+                   head_dim=64, num_res_blocks=2, attn_scales=[1, 0.5, 0.25], dropout=0.1, temporal_attention=True)
+    mine = UNetSD(dim=64)
+    assert {k: tuple(v.shape) for k, v in ref.state_dict().items()} == {k: tuple(v.shape) for k, v in mine.state_dict().items()}
+    kinds = ('Linear', 'Conv1d', 'Conv2d', 'Conv3d')
+    rt = {n: type(x).__name__ for n, x in ref.named_modules() if type(x).__name__ in kinds}
+    mt = {n: type(x).__name__ for n, x in mine.named_modules() if type(x).__name__ in kinds}
+    assert rt == mt
+    rv = m.AutoencoderKL(dict(VAE_DDCONFIG), 4, None)
+    mv = AutoencoderKL(VAE_DDCONFIG, 4)
+    assert {k: tuple(v.shape) for k, v in rv.state_dict().items()} == {k: tuple(v.shape) for k, v in mv.state_dict().items()}

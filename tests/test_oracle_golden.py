@@ -1,0 +1,98 @@
+"""CPU: the oracle restatement reproduces the committed reference outputs (tests/golden/*.pt, produced by
+oracle/make_golden.py from the UNMODIFIED reference).  When /root/reference is mounted, the restatement is also
+re-checked live against the reference modules."""
+import os
+
+import pytest
+import torch
+
+from oracle import unet_oracle as UO, vae_oracle as VO, samplers_oracle as SO
+from oracle import ref_shim
+from oracle.make_golden import analytic_model, _SchedModel, synth_inputs
+
+
+def test_unet_tiny_matches_reference_fixture(gold_dir):
+    g = torch.load(os.path.join(gold_dir, 'unet_tiny.pt'))
+    cfg = UO.UNetConfig(**{**g['cfg'], 'dim_mult': tuple(g['cfg']['dim_mult']), 'attn_scales': tuple(g['cfg']['attn_scales'])})
+    W = UO.make_weights(UO.param_specs(cfg), seed=g['wseed'])
+    x, c, uc = synth_inputs(g['F'], g['h'], g['w'])
+    taps = {}
+    out = UO.unet_forward(W, cfg, x, torch.tensor([g['t']]), c, taps)
+    assert torch.allclose(out, g['eps_cond'], rtol=0, atol=2e-5)
+    assert torch.allclose(UO.unet_forward(W, cfg, x, torch.tensor([g['t']]), uc), g['eps_uncond'], rtol=0, atol=2e-5)
+    ntap = 0
+    for k, v in g.items():
+        if k.startswith('tap:'):
+            assert torch.allclose(taps[k[4:]].half().float(), v.float(), rtol=2e-3, atol=2e-3), k
+            ntap += 1
+    assert ntap >= 10
+
+
+def test_param_specs_count_public_config():
+    specs = UO.param_specs(UO.UNetConfig())
+    assert len(specs) == 1480
+    n = sum(int(torch.tensor(s).prod()) for s in specs.values())
+    assert abs(n / 1e6 - 1411.23) < 0.5                         # 1.41 B parameters
+
+
+def test_vae_decode_matches_reference_fixture(gold_dir):
+    g = torch.load(os.path.join(gold_dir, 'vae_decode.pt'))
+    cfg = VO.VAEConfig()
+    W = UO.make_weights(VO.decoder_param_specs(cfg), seed=g['wseed'])
+    z = torch.randn(g['z_shape'], generator=torch.Generator('cpu').manual_seed(g['z_seed'])) * g['z_scale']
+    out = VO.vae_decode(W, cfg, z)
+    assert torch.allclose(out, g['out'], rtol=0, atol=1e-4)
+
+
+@pytest.mark.parametrize('key,fn,S,scale', [
+    ('ddim_gaussian_S50_g17.0', SO.ddim_gaussian_sample, 50, 17.0),
+    ('ddim_gaussian_S20_g7.5', SO.ddim_gaussian_sample, 20, 7.5),
+    ('ddim_gaussian_S7_g1.0', SO.ddim_gaussian_sample, 7, 1.0),
+    ('ddim_S50_g17.0', SO.ddim_sample, 50, 17.0),
+    ('ddim_S20_g7.5', SO.ddim_sample, 20, 7.5),
+    ('ddim_S7_g1.0', SO.ddim_sample, 7, 1.0),
+    ('unipc_S30_g17.0', SO.unipc_sample, 30, 17.0),
+    ('unipc_S12_g7.5', SO.unipc_sample, 12, 7.5),
+    ('unipc_S5_g1.0', SO.unipc_sample, 5, 1.0),
+])
+def test_sampler_trajectories_match_reference_fixture(gold_dir, key, fn, S, scale):
+    g = torch.load(os.path.join(gold_dir, 'samplers.pt'))
+    betas = SO.linear_sd_betas()
+    x = torch.randn(g['shape'], generator=torch.Generator('cpu').manual_seed(g['x_seed']))
+    c = torch.full((1, 77, 8), g['c_val'])
+    uc = torch.full((1, 77, 8), g['uc_val'])
+    torch.manual_seed(7)
+    out = fn(_SchedModel(betas), betas, x, S, c, uc, scale)
+    assert torch.allclose(out, g[key], rtol=0, atol=1e-6), (out - g[key]).abs().max()
+
+
+def test_gaussian_cfg_guides_only_first_half_of_channels():
+    """cond = 1, uncond = 0, g = 17 -> [17, 17, 1, 1]."""
+    y = torch.ones(1, 4, 2, 2, 2)
+    u = torch.zeros(1, 4, 2, 2, 2)
+    out = SO.gaussian_cfg(y, u, 17.0)
+    assert out[0, :, 0, 0, 0].tolist() == [17.0, 17.0, 1.0, 1.0]
+
+
+def test_ddim_timestep_grids():
+    ts, stride = SO.gaussian_timesteps(1000, 50)
+    assert ts[0] == 981 and ts[-1] == 1 and stride == 20 and len(ts) == 50
+    dts, *_ = SO.ddim_schedule(torch.cumprod(1 - SO.linear_sd_betas(), 0), 50)
+    assert dts[0] == 1 and dts[-1] == 981
+
+
+@pytest.mark.skipif(not ref_shim.reference_available(), reason='reference tree not mounted')
+def test_oracle_unet_live_against_reference():
+    m = ref_shim.load_modelscope()
+    cfg = UO.UNetConfig(dim=64)
+    net = m.UNetSD(in_dim=4, dim=64, y_dim=768, context_dim=1024, out_dim=4, dim_mult=[1, 2, 4, 4], num_heads=8,
+                   head_dim=64, num_res_blocks=2, attn_scales=[1, 0.5, 0.25], dropout=0.1, temporal_attention=True).eval()
+    W = UO.make_weights(UO.param_specs(cfg), seed=5)
+    net.load_state_dict(W, strict=True)
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(2, 4, 3, 8, 8, generator=g)
+    y = torch.randn(2, 77, 1024, generator=g)
+    t = torch.tensor([500, 20])
+    with torch.no_grad():
+        ref = net(x, t, y)
+    assert torch.allclose(UO.unet_forward(W, cfg, x, t, y), ref, rtol=0, atol=3e-5)
