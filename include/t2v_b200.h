@@ -69,6 +69,11 @@ int t2v_unet_forward(t2v_unet* u, const void* x, int x_is_f32, const float* t, c
 /* 2*MAC flop count of one forward at this shape (for roofline reporting). */
 double t2v_unet_flops(t2v_unet* u, int B, int F, int h, int w, int L);
 int t2v_unet_num_launches(t2v_unet* u);
+/* Measurement aid: replays the plan of this shape once (inputs = whatever the last forward left in the staging
+ * buffers) with a CUDA-event pair around every launch on `stream` and sums per kernel family:
+ *   out[3k + 0] = milliseconds, out[3k + 1] = algorithmic flop, out[3k + 2] = launches, k = 0 implicit-GEMM (tcgen05),
+ *   1 attention, 2 group/layer norm, 3 glue; out[12] = total ms.  Synchronises the stream (bench/tests only).   */
+int t2v_unet_profile(t2v_unet* u, int B, int F, int h, int w, int L, void* stream, double* out13);
 /* copies an internal activation (debug / parity taps): name = reference module path (e.g. "input_blocks.1.0"),
  * dst receives [(B F), C, h, w] fp16 as the reference module returns it. Returns element count or <0. */
 long long t2v_unet_read_tap(t2v_unet* u, const char* name, void* dst, long long cap_elems, void* stream);

@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+#include <cstdlib>
 #include <cstring>
 
 namespace t2v {
@@ -209,14 +210,49 @@ int Builder::gemm(GemmProblem& p) {
         error = rc;
         return rc;
     }
-    plan_->steps.push_back([gp](cudaStream_t s) { return gemm_launch(gp, s); });
+    char lab[192];
+    snprintf(lab, sizeof(lab), "gemm rows=%.0f N=%d K=%d taps=%d bn=%d tiles=%dx%d grid=%d%s%s", rows, p.N, p.K, p.ntaps, gp.bn,
+             gp.desc.tiles_m, gp.desc.tiles_n, gp.grid, (p.flags & GEMM_GEGLU) ? " geglu" : "", p.residual ? " +res" : "");
+    plan_->steps.push_back(StepRec{[gp](cudaStream_t s) { return gemm_launch(gp, s); }, STEP_GEMM, gp.flops, lab});
     plan_->launches += 1;
     return 0;
 }
 
-void Builder::step(Step s, int launches) {
+void Builder::step(Step s, int launches, int kind, double flops, const char* label) {
     plan_->launches += launches;
-    if (!dry_) plan_->steps.push_back(std::move(s));
+    plan_->flops += flops;
+    if (!dry_) plan_->steps.push_back(StepRec{std::move(s), kind, flops, label});
+}
+
+int profile_plan(Plan* plan, cudaStream_t stream, double* out13) {
+    const size_t n = plan->steps.size();
+    std::vector<cudaEvent_t> ev(n + 1);
+    for (auto& e : ev) cudaEventCreate(&e);
+    cudaEventRecord(ev[0], stream);
+    int rc = 0;
+    for (size_t i = 0; i < n && rc == 0; ++i) {
+        rc = plan->steps[i].fn(stream);
+        cudaEventRecord(ev[i + 1], stream);
+    }
+    cudaStreamSynchronize(stream);
+    for (int i = 0; i < 13; ++i) out13[i] = 0.0;
+    if (rc == 0) {
+        FILE* f = nullptr;
+        if (const char* path = getenv("T2V_PROFILE_DUMP")) f = fopen(path, "w");
+        for (size_t i = 0; i < n; ++i) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, ev[i], ev[i + 1]);
+            const int k = plan->steps[i].kind;
+            out13[k * 3 + 0] += ms;
+            out13[k * 3 + 1] += plan->steps[i].flops;
+            out13[k * 3 + 2] += 1.0;
+            out13[12] += ms;
+            if (f) fprintf(f, "%zu\t%d\t%.4f\t%.4g\t%s\n", i, k, ms, plan->steps[i].flops, plan->steps[i].label.c_str());
+        }
+        if (f) fclose(f);
+    }
+    for (auto& e : ev) cudaEventDestroy(e);
+    return rc;
 }
 
 void taps_3x3(GemmProblem& p) {
@@ -397,7 +433,7 @@ Tok group_norm(NetCtx& c, const Tok& x, const std::string& prefix, long long row
     c.b->step([=](cudaStream_t s) {
         return groupnorm_silu(xx.p, xx.ld, y.p, y.ld, xx.rows, xx.C, static_cast<int>(rows_per_inst), g, bt, eps, silu ? 1 : 0,
                               ws, sms, s);
-    }, 2);
+    }, 2, STEP_NORM, 0.0, "groupnorm");
     return y;
 }
 
@@ -406,7 +442,7 @@ Tok layer_norm(NetCtx& c, const Tok& x, const std::string& prefix) {
     const __half* g = prm(c, prefix + ".weight");
     const __half* bt = prm(c, prefix + ".bias");
     const Tok xx = x;
-    c.b->step([=](cudaStream_t s) { return layernorm(xx.p, xx.ld, y.p, y.ld, xx.rows, xx.C, g, bt, 1e-5f, s); });
+    c.b->step([=](cudaStream_t s) { return layernorm(xx.p, xx.ld, y.p, y.ld, xx.rows, xx.C, g, bt, 1e-5f, s); }, 1, STEP_NORM, 0.0, "layernorm");
     return y;
 }
 

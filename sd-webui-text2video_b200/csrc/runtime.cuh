@@ -74,9 +74,16 @@ struct Tok {                      // channels-last token matrix view
 };
 
 using Step = std::function<int(cudaStream_t)>;
+enum StepKind : int { STEP_GEMM = 0, STEP_ATTN = 1, STEP_NORM = 2, STEP_OTHER = 3, STEP_NKINDS = 4 };
+struct StepRec {
+    Step fn;
+    int kind;
+    double flops;
+    std::string label;
+};
 
 struct Plan {
-    std::vector<Step> steps;
+    std::vector<StepRec> steps;
     char* slab = nullptr;
     size_t slab_bytes = 0;
     double flops = 0.0;
@@ -97,7 +104,7 @@ public:
     void free(const Tok& t) { arena_->free(reinterpret_cast<char*>(t.p)); }
     void free_bytes(void* p) { arena_->free(reinterpret_cast<char*>(p)); }
     int gemm(GemmProblem& p);                                     // plans + records; returns 0 or <0
-    void step(Step s, int launches = 1);
+    void step(Step s, int launches = 1, int kind = STEP_OTHER, double flops = 0.0, const char* label = "");
     void add_flops(double f) { plan_->flops += f; }
     int sms() const { return sms_; }
     int error = 0;
@@ -131,6 +138,10 @@ Tok group_norm(NetCtx& c, const Tok& x, const std::string& prefix, long long row
 Tok layer_norm(NetCtx& c, const Tok& x, const std::string& prefix);
 Tok conv3x3(NetCtx& c, const Tok& x, const std::string& wname, const __half* bias, int bias_rows, long long bias_stride,
             int N, int hcur, int wcur, const Tok* residual, int n_alloc = 0);
+
+// Runs the plan once with a CUDA-event pair around every step; out[kind*3 + {0,1,2}] = {ms, flops, launches}, out[12] = total ms.
+// If T2V_PROFILE_DUMP names a file, one line per launch (index, kind, ms, flop, label) is written there.
+int profile_plan(Plan* plan, cudaStream_t stream, double* out13);
 
 // conv taps helpers over row dims (w, h, frames) and (pixels, frames, samples)
 void taps_3x3(GemmProblem& p);

@@ -303,8 +303,9 @@ Tok transformer_block(Ctx& c, Tok x, const std::string& p, int heads, int hcur, 
         c.b->free(l);
         {
             const AttnParams apc = ap_;
-            c.b->step([apc](cudaStream_t s) { return attention(apc, s); });
-            c.b->add_flops(4.0 * apc.batch * apc.heads * static_cast<double>(apc.sq) * apc.skv * 64);
+            c.b->step([apc](cudaStream_t s) { return attention(apc, s); }, 1, STEP_ATTN,
+                      4.0 * apc.batch * apc.heads * static_cast<double>(apc.sq) * apc.skv * 64,
+                      temporal ? "attn temporal" : (self_attn ? "attn spatial" : "attn cross"));
         }
         c.b->free(qkv);
         if (!self_attn) c.b->free(kv);
@@ -679,7 +680,7 @@ int t2v_unet_forward(t2v_unet* u, const void* x, int x_is_f32, const float* t, c
     cudaMemcpyAsync(io.ctx, ctx, static_cast<size_t>(B) * L * cfg.context_dim * sizeof(__half), cudaMemcpyDeviceToDevice,
                     stream);
     for (auto& s : plan->steps) {
-        rc = s(stream);
+        rc = s.fn(stream);
         if (rc != 0) {
             set_error("UNet launch failed (%d): %s", rc, cudaGetErrorString(cudaGetLastError()));
             return rc;
@@ -700,6 +701,13 @@ double t2v_unet_flops(t2v_unet* u, int B, int F, int h, int w, int L) {
 }
 
 int t2v_unet_num_launches(t2v_unet* u) { return u->last_launches; }
+
+int t2v_unet_profile(t2v_unet* u, int B, int F, int h, int w, int L, void* stream_, double* out13) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    Plan* plan = get_plan(u, B, F, h, w, L, stream);
+    if (!plan) return -1;
+    return profile_plan(plan, stream, out13);
+}
 
 int t2v_unet_enable_taps(t2v_unet* u, int on) {
     u->taps_enabled = on != 0;

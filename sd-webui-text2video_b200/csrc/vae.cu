@@ -320,7 +320,7 @@ int t2v_vae_decode(t2v_vae* v, const void* z, int z_is_f32, float z_scale, void*
     int rc = ingest_latent(z, z_is_f32, io.z_tok, zpad, zpad, B, v->cfg.z_channels, F, h, w, z_scale, stream);
     if (rc != 0) return rc;
     for (auto& s : plan->steps) {
-        rc = s(stream);
+        rc = s.fn(stream);
         if (rc != 0) {
             set_error("VAE launch failed (%d): %s", rc, cudaGetErrorString(cudaGetLastError()));
             return rc;

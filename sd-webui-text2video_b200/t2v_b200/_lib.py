@@ -26,6 +26,7 @@ SIGNATURES = {
     't2v_unet_forward': (c_int, [P, P, c_int, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     't2v_unet_flops': (c_double, [P, c_int, c_int, c_int, c_int, c_int]),
     't2v_unet_num_launches': (c_int, [P]),
+    't2v_unet_profile': (c_int, [P, c_int, c_int, c_int, c_int, c_int, P, C.POINTER(c_double)]),
     't2v_unet_read_tap': (c_ll, [P, c_char_p, P, c_ll, P]),
     't2v_unet_enable_taps': (c_int, [P, c_int]),
     't2v_vae_create': (c_int, [P, C.POINTER(P)]),

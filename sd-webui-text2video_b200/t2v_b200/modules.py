@@ -225,6 +225,14 @@ class UNetSD(_NativeModule):
     def num_launches(self):
         return _lib.load_library().t2v_unet_num_launches(self._handle)
 
+    def profile(self, B, F, h, w, L=77):
+        """Per-kernel-family device time of one forward at this shape (CUDA events around every launch)."""
+        out = (C.c_double * 13)()
+        _lib.check(_lib.lib().t2v_unet_profile(self._handle, B, F, h, w, L, _lib.stream_ptr(), out), 'unet_profile')
+        fam = ('gemm', 'attention', 'norm', 'glue')
+        return {**{f: {'ms': out[3 * i], 'flop': out[3 * i + 1], 'launches': int(out[3 * i + 2])} for i, f in enumerate(fam)},
+                'total_ms': out[12]}
+
     def enable_taps(self, on=True):
         _lib.load_library().t2v_unet_enable_taps(self._handle, int(on))
 
