@@ -1,11 +1,11 @@
 // tcgen05 / TMEM / TMA implicit-GEMM kernel (sm_100a).  See gemm_tc.cuh for the data model.
 //
-// Per CTA (persistent, 192 threads, 1 CTA/SM):
+// Per CTA (persistent, 320 threads, 1 CTA/SM):
 //   warp 0      TMA producer  : per k-iteration one A box (128 rows x 64 K, tap-shifted coordinates, OOB = zero
 //                               padding) + one B box (BN x 64 K) into a SWIZZLE_128B smem ring
 //   warp 1      MMA issuer    : lane 0 issues 4 x tcgen05.mma (M=128, N=BN, K=16) per stage into a double-buffered
 //                               fp32 accumulator in TMEM; tcgen05.commit releases the smem stage / publishes the tile
-//   warps 2..5  epilogue      : tcgen05.ld 32 lanes x 32 columns -> registers -> alpha, bias, residual, GEGLU -> HBM
+//   warps 2..9  epilogue      : tcgen05.ld 32 lanes x 32 columns -> registers -> alpha, bias, residual, GEGLU -> HBM
 // Roofline: tensor-bound (2*M*N*K*taps flop per launch) whenever K*taps is large; see DESIGN.md.
 #include "gemm_tc.cuh"
 #include "ptx.cuh"
@@ -18,7 +18,7 @@ namespace t2v {
 
 namespace {
 
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;   // TMA warp + MMA warp + 8 epilogue warps
 constexpr int kABytes = GEMM_BLOCK_M * GEMM_BLOCK_K * 2;   // 16 KB
 constexpr int kSmemBudget = 200 * 1024;                     // ring budget (barriers + alignment slack on top)
 
@@ -32,7 +32,7 @@ struct Cfg {
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
-template <int BN>
+template <int BN, bool GEGLU>
 __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_constant__ GemmDesc g) {
     using C = Cfg<BN>;
     extern __shared__ uint8_t smem_raw[];
@@ -57,8 +57,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         }
         mbar_init(&tfull[0], 1);
         mbar_init(&tfull[1], 1);
-        mbar_init(&tempty[0], 4);
-        mbar_init(&tempty[1], 4);
+        mbar_init(&tempty[0], 8);
+        mbar_init(&tempty[1], 8);
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, 512);   // 2 accumulator stages x 256 fp32 columns
@@ -149,17 +149,25 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
             if (acc == 0) acc_phase ^= 1u;
         }
     } else {
-        // ------------------------------------------------------------------ epilogue (warps 2..5)
-        const int q = warp & 3;                        // TMEM lane quadrant this warp may access
+        // ------------------------------------------------------------------ epilogue (warps 2..9)
+        // 8 warps: TMEM lane quadrant q = warp & 3 (a warp may only touch lanes 32q..32q+31), column chunks are
+        // interleaved between the two warps of a quadrant.  Per chunk the residual row segment is prefetched one
+        // chunk ahead so that HBM/L2 latency overlaps the previous chunk's math and stores.
+        const int q = warp & 3;
+        const int hsel = (warp - 2) >> 2;              // which half of the chunks this warp handles
         const int r = q * 32 + lane;                   // row of the tile held by this thread
         int acc = 0;
         uint32_t acc_phase = 0;
-        const bool geglu = (g.flags & GEMM_GEGLU) != 0;
+        constexpr bool geglu = GEGLU;
         const bool out_f32 = (g.flags & GEMM_OUT_F32) != 0;
         constexpr int CW = BN >= 32 ? 32 : 16;        // columns per tcgen05.ld
+        constexpr int NV = CW / 8;                     // 16-byte vectors per chunk row segment
         const int ncols_tile = geglu ? BN / 2 : BN;
-        const bool vec_ok = ((g.ldo & 7) == 0) && ((g.N & 7) == 0) &&
+        const int nchunks = ncols_tile / CW;
+        const int nvalid = geglu ? g.N / 2 : g.N;
+        const bool vec_ok = ((g.ldo & 7) == 0) && ((g.N & 7) == 0) && (!geglu || (g.N & 15) == 0) &&
                             (g.residual == nullptr || (g.ldr & 7) == 0);
+        const bool bias_vec = (g.bias != nullptr) && ((g.N & 7) == 0) && ((g.bias_stride & 7) == 0);
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const int tn = tile % g.tiles_n;
             int tm = tile / g.tiles_n;
@@ -185,67 +193,106 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
             }
             const __half* bias = g.bias;
             if (bias != nullptr && g.bias_rows > 0) bias += (grow / g.bias_rows) * g.bias_stride;
+            const int ocol0 = geglu ? tn * (BN / 2) : tn * BN;
+            const __half* res_row = (g.residual != nullptr && valid) ? g.residual + grow * g.ldr + ocol0 : nullptr;
+
+            uint4 rnext[NV];
+            auto prefetch_res = [&](int ci) {
+                if (res_row != nullptr && vec_ok) {
+#pragma unroll
+                    for (int k = 0; k < NV; ++k) {
+                        const int col = ci * CW + k * 8;
+                        if (ocol0 + col < nvalid) rnext[k] = __ldg(reinterpret_cast<const uint4*>(res_row + col));
+                    }
+                }
+            };
+            if (hsel < nchunks) prefetch_res(hsel);
 
             mbar_wait(&tfull[acc], acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * 256);
-            for (int c0 = 0; c0 < ncols_tile; c0 += CW) {
-                float v[CW];
-                {
-                    uint32_t u[CW];
-                    if constexpr (CW == 32) tmem_ld_32x32(taddr + c0, u);
-                    else tmem_ld_32x16(taddr + c0, u);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int j = 0; j < CW; ++j) v[j] = __uint_as_float(u[j]) * g.alpha;
-                }
-                const int pcol = tn * BN + c0;                    // packed (accumulator) column of v[0]
-                if (bias != nullptr) {
-#pragma unroll
-                    for (int j = 0; j < CW; ++j)
-                        if (pcol + j < g.N) v[j] += __half2float(__ldg(bias + pcol + j));
-                }
-                int ocol = pcol;
+            for (int ci = hsel; ci < nchunks; ci += 2) {
+                const int c0 = ci * CW;
+                uint32_t u[CW];
+                uint32_t ug[CW];
+                if constexpr (CW == 32) tmem_ld_32x32(taddr + c0, u);
+                else tmem_ld_32x16(taddr + c0, u);
                 if (geglu) {
-                    float gt[CW];
-                    uint32_t u[CW];
-                    if constexpr (CW == 32) tmem_ld_32x32(taddr + BN / 2 + c0, u);
-                    else tmem_ld_32x16(taddr + BN / 2 + c0, u);
-                    tmem_ld_wait();
+                    if constexpr (CW == 32) tmem_ld_32x32(taddr + BN / 2 + c0, ug);
+                    else tmem_ld_32x16(taddr + BN / 2 + c0, ug);
+                }
+                uint4 rcur[NV];
+#pragma unroll
+                for (int k = 0; k < NV; ++k) rcur[k] = rnext[k];
+                if (ci + 2 < nchunks) prefetch_res(ci + 2);
+                const int pcol = tn * BN + c0;                    // packed (accumulator) column of v[0]
+                float bv[CW], bg[CW];
+                if (bias_vec) {
+#pragma unroll
+                    for (int k = 0; k < NV; ++k) {
+                        uint4 t4 = make_uint4(0, 0, 0, 0);
+                        if (pcol + k * 8 < g.N) t4 = __ldg(reinterpret_cast<const uint4*>(bias + pcol + k * 8));
+                        const __half2* h2 = reinterpret_cast<const __half2*>(&t4);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float2 f = __half22float2(h2[e]);
+                            bv[k * 8 + 2 * e] = f.x;
+                            bv[k * 8 + 2 * e + 1] = f.y;
+                        }
+                        if (geglu) {
+                            uint4 g4 = make_uint4(0, 0, 0, 0);
+                            if (pcol + BN / 2 + k * 8 < g.N) g4 = __ldg(reinterpret_cast<const uint4*>(bias + pcol + BN / 2 + k * 8));
+                            const __half2* gh2 = reinterpret_cast<const __half2*>(&g4);
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const float2 f = __half22float2(gh2[e]);
+                                bg[k * 8 + 2 * e] = f.x;
+                                bg[k * 8 + 2 * e + 1] = f.y;
+                            }
+                        }
+                    }
+                } else {
 #pragma unroll
                     for (int j = 0; j < CW; ++j) {
-                        gt[j] = __uint_as_float(u[j]) * g.alpha;
-                        if (bias != nullptr && pcol + BN / 2 + j < g.N) gt[j] += __half2float(__ldg(bias + pcol + BN / 2 + j));
+                        bv[j] = (bias != nullptr && pcol + j < g.N) ? __half2float(__ldg(bias + pcol + j)) : 0.f;
+                        bg[j] = (geglu && bias != nullptr && pcol + BN / 2 + j < g.N) ? __half2float(__ldg(bias + pcol + BN / 2 + j)) : 0.f;
+                    }
+                }
+                tmem_ld_wait();
+                float v[CW];
+#pragma unroll
+                for (int j = 0; j < CW; ++j) v[j] = fmaf(__uint_as_float(u[j]), g.alpha, bv[j]);
+                if (geglu) {
+#pragma unroll
+                    for (int j = 0; j < CW; ++j) {
+                        const float gt = fmaf(__uint_as_float(ug[j]), g.alpha, bg[j]);
                         // reference rounding points (fp16 autocast): proj output, gelu output, product
                         const float xa = __half2float(__float2half_rn(v[j]));
-                        const float ga = __half2float(__float2half_rn(gt[j]));
+                        const float ga = __half2float(__float2half_rn(gt));
                         const float ge = __half2float(__float2half_rn(gelu_erf(ga)));
                         v[j] = xa * ge;
                     }
-                    ocol = tn * (BN / 2) + c0;
                 }
-                const int nvalid = geglu ? g.N / 2 : g.N;
+                const int ocol = ocol0 + c0;
                 if (valid) {
-                    if (g.residual != nullptr) {
-                        const __half* rp = g.residual + grow * g.ldr + ocol;
+                    if (res_row != nullptr) {
                         if (vec_ok) {
 #pragma unroll
-                            for (int j = 0; j < CW; j += 8) {
-                                if (ocol + j < nvalid) {
-                                    const uint4 rv = __ldg(reinterpret_cast<const uint4*>(rp + j));
-                                    const __half2* h2 = reinterpret_cast<const __half2*>(&rv);
+                            for (int k = 0; k < NV; ++k) {
+                                if (ocol + k * 8 < nvalid) {
+                                    const __half2* h2 = reinterpret_cast<const __half2*>(&rcur[k]);
 #pragma unroll
                                     for (int e = 0; e < 4; ++e) {
                                         const float2 f = __half22float2(h2[e]);
-                                        v[j + 2 * e] += f.x;
-                                        v[j + 2 * e + 1] += f.y;
+                                        v[k * 8 + 2 * e] += f.x;
+                                        v[k * 8 + 2 * e + 1] += f.y;
                                     }
                                 }
                             }
                         } else {
 #pragma unroll
                             for (int j = 0; j < CW; ++j)
-                                if (ocol + j < nvalid) v[j] += __half2float(rp[j]);
+                                if (ocol + j < nvalid) v[j] += __half2float(res_row[c0 + j]);
                         }
                     }
                     if (out_f32) {
@@ -257,13 +304,13 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
                         __half* op = reinterpret_cast<__half*>(g.out) + grow * g.ldo + ocol;
                         if (vec_ok) {
 #pragma unroll
-                            for (int j = 0; j < CW; j += 8) {
-                                if (ocol + j < nvalid) {
+                            for (int k = 0; k < NV; ++k) {
+                                if (ocol + k * 8 < nvalid) {
                                     uint4 ov;
                                     __half2* h2 = reinterpret_cast<__half2*>(&ov);
 #pragma unroll
-                                    for (int e = 0; e < 4; ++e) h2[e] = __floats2half2_rn(v[j + 2 * e], v[j + 2 * e + 1]);
-                                    *reinterpret_cast<uint4*>(op + j) = ov;
+                                    for (int e = 0; e < 4; ++e) h2[e] = __floats2half2_rn(v[k * 8 + 2 * e], v[k * 8 + 2 * e + 1]);
+                                    *reinterpret_cast<uint4*>(op + k * 8) = ov;
                                 }
                             }
                         } else {
@@ -315,8 +362,12 @@ int encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dim
 
 template <int BN>
 int set_attr() {
-    return cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                Cfg<BN>::kSmemBytes) == cudaSuccess ? 0 : -1;
+    if (cudaFuncSetAttribute(gemm_tc_kernel<BN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             Cfg<BN>::kSmemBytes) != cudaSuccess) return -1;
+    if (BN >= 64 && BN != 160)
+        if (cudaFuncSetAttribute(gemm_tc_kernel<(BN >= 64 && BN != 160) ? BN : 64, true>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::kSmemBytes) != cudaSuccess) return -1;
+    return 0;
 }
 
 }  // namespace
@@ -467,13 +518,23 @@ int gemm_plan(const GemmProblem& p, GemmPlan* plan, int num_sms) {
 }
 
 int gemm_launch(const GemmPlan& plan, cudaStream_t stream) {
-    switch (plan.bn) {
-        case 16: gemm_tc_kernel<16><<<plan.grid, kThreads, plan.smem, stream>>>(plan.desc); break;
-        case 64: gemm_tc_kernel<64><<<plan.grid, kThreads, plan.smem, stream>>>(plan.desc); break;
-        case 128: gemm_tc_kernel<128><<<plan.grid, kThreads, plan.smem, stream>>>(plan.desc); break;
-        case 160: gemm_tc_kernel<160><<<plan.grid, kThreads, plan.smem, stream>>>(plan.desc); break;
-        case 256: gemm_tc_kernel<256><<<plan.grid, kThreads, plan.smem, stream>>>(plan.desc); break;
-        default: return -1;
+    const bool geglu = (plan.desc.flags & GEMM_GEGLU) != 0;
+    if (geglu) {
+        switch (plan.bn) {
+            case 64: gemm_tc_kernel<64, true><<<plan.grid, kThreads, plan.smem, stream>>>(plan.desc); break;
+            case 128: gemm_tc_kernel<128, true><<<plan.grid, kThreads, plan.smem, stream>>>(plan.desc); break;
+            case 256: gemm_tc_kernel<256, true><<<plan.grid, kThreads, plan.smem, stream>>>(plan.desc); break;
+            default: return -1;
+        }
+    } else {
+        switch (plan.bn) {
+            case 16: gemm_tc_kernel<16, false><<<plan.grid, kThreads, plan.smem, stream>>>(plan.desc); break;
+            case 64: gemm_tc_kernel<64, false><<<plan.grid, kThreads, plan.smem, stream>>>(plan.desc); break;
+            case 128: gemm_tc_kernel<128, false><<<plan.grid, kThreads, plan.smem, stream>>>(plan.desc); break;
+            case 160: gemm_tc_kernel<160, false><<<plan.grid, kThreads, plan.smem, stream>>>(plan.desc); break;
+            case 256: gemm_tc_kernel<256, false><<<plan.grid, kThreads, plan.smem, stream>>>(plan.desc); break;
+            default: return -1;
+        }
     }
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }

@@ -42,6 +42,7 @@ __global__ void __launch_bounds__(kStatsThreads) gn_stats_kernel(const __half* _
 #pragma unroll
         for (int e = 0; e < 8; ++e) s[e] = q[e] = 0.f;
         if (vc < C8) {
+#pragma unroll 4
             for (int r = r0 + ty; r < r1; r += 8) {
                 const uint4 v = __ldg(reinterpret_cast<const uint4*>(base + r * ld + vc * 8));
                 const __half2* h2 = reinterpret_cast<const __half2*>(&v);
@@ -115,36 +116,55 @@ __global__ void __launch_bounds__(kStatsThreads) gn_stats_kernel(const __half* _
 
 __device__ __forceinline__ float silu_f(float v) { return v / (1.0f + __expf(-v)); }
 
+// grid = (row blocks, instances).  Each block first folds (mean, rstd, gamma, beta) of ITS instance into per-channel
+// scale/shift in smem, then streams its rows: y = act(x * a[c] + b[c]) -- one FMA per element, 16-byte accesses.
 __global__ void __launch_bounds__(256) gn_apply_kernel(const __half* __restrict__ x, long long ldx,
-                                                       __half* __restrict__ y, long long ldy, long long rows, int C,
-                                                       int rows_per_inst, const float2* __restrict__ stats,
+                                                       __half* __restrict__ y, long long ldy, int C,
+                                                       int rows_per_inst, int rows_per_block,
+                                                       const float2* __restrict__ stats,
                                                        const __half* __restrict__ gamma,
                                                        const __half* __restrict__ beta, int silu) {
+    extern __shared__ float ab[];          // a[C] | b[C]
+    const int inst = blockIdx.y;
     const int C8 = C >> 3;
     const int cpg = C / kGroups;
-    const long long total = rows * C8;
-    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
-         i += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const long long r = i / C8;
-        const int vc = static_cast<int>(i - r * C8);
-        const int inst = static_cast<int>(r / rows_per_inst);
-        const uint4 v = __ldg(reinterpret_cast<const uint4*>(x + r * ldx + vc * 8));
-        const uint4 gv = __ldg(reinterpret_cast<const uint4*>(gamma + vc * 8));
-        const uint4 bv = __ldg(reinterpret_cast<const uint4*>(beta + vc * 8));
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const float2 ms = __ldg(stats + inst * kGroups + c / cpg);
+        const float a = ms.y * __half2float(__ldg(gamma + c));
+        ab[c] = a;
+        ab[C + c] = __half2float(__ldg(beta + c)) - ms.x * a;
+    }
+    __syncthreads();
+    const int r0 = blockIdx.x * rows_per_block;
+    const int r1 = min(r0 + rows_per_block, rows_per_inst);
+    const long long base_row = static_cast<long long>(inst) * rows_per_inst;
+    const int total = (r1 - r0) * C8;
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+        const int r = i / C8;
+        const int vc = i - r * C8;
+        const long long row = base_row + r0 + r;
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(x + row * ldx + vc * 8));
         const __half* xh = reinterpret_cast<const __half*>(&v);
-        const __half* gh = reinterpret_cast<const __half*>(&gv);
-        const __half* bh = reinterpret_cast<const __half*>(&bv);
+        const float4 a0 = *reinterpret_cast<const float4*>(ab + vc * 8);
+        const float4 a1 = *reinterpret_cast<const float4*>(ab + vc * 8 + 4);
+        const float4 b0 = *reinterpret_cast<const float4*>(ab + C + vc * 8);
+        const float4 b1 = *reinterpret_cast<const float4*>(ab + C + vc * 8 + 4);
+        float f[8] = {fmaf(__half2float(xh[0]), a0.x, b0.x), fmaf(__half2float(xh[1]), a0.y, b0.y),
+                      fmaf(__half2float(xh[2]), a0.z, b0.z), fmaf(__half2float(xh[3]), a0.w, b0.w),
+                      fmaf(__half2float(xh[4]), a1.x, b1.x), fmaf(__half2float(xh[5]), a1.y, b1.y),
+                      fmaf(__half2float(xh[6]), a1.z, b1.z), fmaf(__half2float(xh[7]), a1.w, b1.w)};
         uint4 o;
-        __half* oh = reinterpret_cast<__half*>(&o);
-        const float2* st = stats + inst * kGroups;
+        __half2* oh = reinterpret_cast<__half2*>(&o);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            const float2 ms = __ldg(st + (vc * 8 + e) / cpg);
-            float f = (__half2float(xh[e]) - ms.x) * ms.y * __half2float(gh[e]) + __half2float(bh[e]);
-            if (silu) f = silu_f(f);
-            oh[e] = __float2half_rn(f);
+        for (int e = 0; e < 4; ++e) {
+            float u0 = f[2 * e], u1 = f[2 * e + 1];
+            if (silu) {
+                u0 = silu_f(u0);
+                u1 = silu_f(u1);
+            }
+            oh[e] = __floats2half2_rn(u0, u1);
         }
-        *reinterpret_cast<uint4*>(y + r * ldy + vc * 8) = o;
+        *reinterpret_cast<uint4*>(y + row * ldy + vc * 8) = o;
     }
 }
 
@@ -247,12 +267,15 @@ int groupnorm_silu(const __half* x, long long ldx, __half* y, long long ldy, lon
     float2* partial = stats + static_cast<size_t>(n_inst) * kGroups;
     gn_stats_kernel<<<dim3(nchunks, n_inst), kStatsThreads, 2 * C * sizeof(float), stream>>>(
         x, ldx, C, rows_per_inst, rpc, nchunks, eps, partial, counters, stats);
-    const long long total = rows * (C / 8);
-    long long blocks = (total + 255) / 256;
-    const long long cap = static_cast<long long>(num_sms) * 16;
-    if (blocks > cap) blocks = cap;
-    gn_apply_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(x, ldx, y, ldy, rows, C, rows_per_inst, stats, gamma,
-                                                                  beta, silu);
+    // rows per apply block: ~8 blocks per SM overall, at least 4 rows
+    long long want_blocks = static_cast<long long>(num_sms) * 8;
+    long long per_inst = (want_blocks + n_inst - 1) / n_inst;
+    if (per_inst < 1) per_inst = 1;
+    long long rpb = (rows_per_inst + per_inst - 1) / per_inst;
+    if (rpb < 4) rpb = 4;
+    const int nblk = static_cast<int>((rows_per_inst + rpb - 1) / rpb);
+    gn_apply_kernel<<<dim3(nblk, n_inst), 256, 2 * C * sizeof(float), stream>>>(x, ldx, y, ldy, C, rows_per_inst,
+                                                                              static_cast<int>(rpb), stats, gamma, beta, silu);
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 

@@ -255,6 +255,40 @@ int profile_plan(Plan* plan, cudaStream_t stream, double* out13) {
     return rc;
 }
 
+int run_plan(Plan* plan, cudaStream_t stream, bool allow_graph) {
+    static const bool graphs = getenv("T2V_NO_GRAPH") == nullptr;
+    if (graphs && allow_graph) {
+        if (plan->graph == nullptr && plan->eager_runs >= 1) {
+            cudaStream_t cs = nullptr;
+            if (cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking) == cudaSuccess) {
+                if (cudaStreamBeginCapture(cs, cudaStreamCaptureModeRelaxed) == cudaSuccess) {
+                    int rc = 0;
+                    for (auto& s : plan->steps) {
+                        rc = s.fn(cs);
+                        if (rc != 0) break;
+                    }
+                    cudaGraph_t g = nullptr;
+                    const cudaError_t e = cudaStreamEndCapture(cs, &g);
+                    if (rc == 0 && e == cudaSuccess && g != nullptr) {
+                        if (cudaGraphInstantiate(&plan->graph, g, 0) != cudaSuccess) plan->graph = nullptr;
+                    }
+                    if (g) cudaGraphDestroy(g);
+                }
+                cudaStreamDestroy(cs);
+            }
+            cudaGetLastError();
+            if (plan->graph == nullptr) plan->eager_runs = -(1 << 30);      // capture failed: stay eager, do not retry
+        }
+        if (plan->graph != nullptr) return cudaGraphLaunch(plan->graph, stream) == cudaSuccess ? 0 : -20;
+    }
+    for (auto& s : plan->steps) {
+        const int rc = s.fn(stream);
+        if (rc != 0) return rc;
+    }
+    plan->eager_runs += 1;
+    return 0;
+}
+
 void taps_3x3(GemmProblem& p) {
     p.ntaps = 9;
     for (int ky = 0; ky < 3; ++ky)

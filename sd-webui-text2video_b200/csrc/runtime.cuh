@@ -91,6 +91,7 @@ struct Plan {
     unsigned long long weights_version = 0;
     std::map<std::string, std::pair<Tok, std::pair<int, int>>> taps;    // name -> (tokens, (h, w))
     cudaGraphExec_t graph = nullptr;
+    int eager_runs = 0;
     ~Plan();
 };
 
@@ -142,6 +143,10 @@ Tok conv3x3(NetCtx& c, const Tok& x, const std::string& wname, const __half* bia
 // Runs the plan once with a CUDA-event pair around every step; out[kind*3 + {0,1,2}] = {ms, flops, launches}, out[12] = total ms.
 // If T2V_PROFILE_DUMP names a file, one line per launch (index, kind, ms, flop, label) is written there.
 int profile_plan(Plan* plan, cudaStream_t stream, double* out13);
+// Replays the plan on `stream`.  The first call runs launch by launch; the second call captures the launch list into a
+// CUDA graph (through a private capture stream: the caller's may be the legacy default stream) and from then on a
+// forward is ONE cudaGraphLaunch -- the ~1k launches stop costing host time.  T2V_NO_GRAPH=1 disables it.
+int run_plan(Plan* plan, cudaStream_t stream, bool allow_graph);
 
 // conv taps helpers over row dims (w, h, frames) and (pixels, frames, samples)
 void taps_3x3(GemmProblem& p);

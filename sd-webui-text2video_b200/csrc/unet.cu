@@ -679,12 +679,10 @@ int t2v_unet_forward(t2v_unet* u, const void* x, int x_is_f32, const float* t, c
     cudaMemcpyAsync(io.t, t, sizeof(float) * B, cudaMemcpyDeviceToDevice, stream);
     cudaMemcpyAsync(io.ctx, ctx, static_cast<size_t>(B) * L * cfg.context_dim * sizeof(__half), cudaMemcpyDeviceToDevice,
                     stream);
-    for (auto& s : plan->steps) {
-        rc = s.fn(stream);
-        if (rc != 0) {
-            set_error("UNet launch failed (%d): %s", rc, cudaGetErrorString(cudaGetLastError()));
-            return rc;
-        }
+    rc = run_plan(plan, stream, !u->taps_enabled);
+    if (rc != 0) {
+        set_error("UNet launch failed (%d): %s", rc, cudaGetErrorString(cudaGetLastError()));
+        return rc;
     }
     u->last_launches = plan->launches + 2;
     const int out_ld = (cfg.out_dim % 8 == 0) ? cfg.out_dim : (cfg.out_dim + 7) / 8 * 8;

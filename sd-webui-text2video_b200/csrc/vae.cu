@@ -319,12 +319,10 @@ int t2v_vae_decode(t2v_vae* v, const void* z, int z_is_f32, float z_scale, void*
     const int zpad = (v->cfg.z_channels + 7) / 8 * 8;
     int rc = ingest_latent(z, z_is_f32, io.z_tok, zpad, zpad, B, v->cfg.z_channels, F, h, w, z_scale, stream);
     if (rc != 0) return rc;
-    for (auto& s : plan->steps) {
-        rc = s.fn(stream);
-        if (rc != 0) {
-            set_error("VAE launch failed (%d): %s", rc, cudaGetErrorString(cudaGetLastError()));
-            return rc;
-        }
+    rc = run_plan(plan, stream, true);
+    if (rc != 0) {
+        set_error("VAE launch failed (%d): %s", rc, cudaGetErrorString(cudaGetLastError()));
+        return rc;
     }
     const int H = h * 8, W = w * 8;       // 3 upsamples for the 4-level decoder
     int up = 1;
