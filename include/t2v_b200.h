@@ -123,7 +123,7 @@ int t2v_lincomb(float* out, const float* const* src, const float* coef, int n_sr
 int t2v_op_gemm(const void* a, long long lda, int K, int nd, const int* dims, int ntaps, const int* tap_off,
                 const void* w_packed, int n_alloc, int N, int b_batch_dim, int flags, void* out, long long ldo,
                 const void* bias, int bias_rows, long long bias_stride, const void* residual, long long ldr,
-                float alpha, int force_bn, void* stream);
+                float alpha, int force_bn, int force_cg, void* stream);
 int t2v_op_pack_conv_weight(const void* src, int src_is_f32, void* dst, int Cout, int Cin, int taps, int n_alloc,
                             int k_alloc, void* stream);
 int t2v_op_pack_geglu_weight(const void* w, const void* b, int src_is_f32, void* wdst, void* bdst, int H, int K, int bn,

@@ -70,7 +70,7 @@ const char* t2v_version(void) { return "t2v_b200 0.1 (sm_100a; tcgen05+TMA impli
 int t2v_op_gemm(const void* a, long long lda, int K, int nd, const int* dims, int ntaps, const int* tap_off,
                 const void* w_packed, int n_alloc, int N, int b_batch_dim, int flags, void* out, long long ldo,
                 const void* bias, int bias_rows, long long bias_stride, const void* residual, long long ldr,
-                float alpha, int force_bn, void* stream) {
+                float alpha, int force_bn, int force_cg, void* stream) {
     GemmProblem p;
     memset(&p, 0, sizeof(p));
     p.a = reinterpret_cast<const __half*>(a);
@@ -95,6 +95,7 @@ int t2v_op_gemm(const void* a, long long lda, int K, int nd, const int* dims, in
     p.ldr = ldr;
     p.alpha = alpha;
     p.force_bn = force_bn;
+    p.force_cg = force_cg;
     GemmPlan plan;
     int rc = gemm_plan(p, &plan, g_num_sms);
     if (rc != 0) {

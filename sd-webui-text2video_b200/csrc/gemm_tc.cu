@@ -12,6 +12,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 namespace t2v {
@@ -22,9 +23,9 @@ constexpr int kThreads = 320;   // TMA warp + MMA warp + 8 epilogue warps
 constexpr int kABytes = GEMM_BLOCK_M * GEMM_BLOCK_K * 2;   // 16 KB
 constexpr int kSmemBudget = 200 * 1024;                     // ring budget (barriers + alignment slack on top)
 
-template <int BN>
+template <int BN, int CG>
 struct Cfg {
-    static constexpr int kBBytes = BN * GEMM_BLOCK_K * 2;
+    static constexpr int kBBytes = (BN / CG) * GEMM_BLOCK_K * 2;      // a CTA of a pair stages half of the B tile
     static constexpr int kStageBytes = kABytes + kBBytes;
     static constexpr int kStages = (kSmemBudget / kStageBytes) > 8 ? 8 : (kSmemBudget / kStageBytes);
     static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
@@ -32,9 +33,11 @@ struct Cfg {
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
-template <int BN, bool GEGLU>
+template <int BN, bool GEGLU, int CG>
 __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_constant__ GemmDesc g) {
-    using C = Cfg<BN>;
+    using C = Cfg<BN, CG>;
+    const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;      // position in the CTA pair
+    const bool leader = rank == 0;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);      // SWIZZLE_128B atoms need 1024 B alignment
@@ -57,17 +60,25 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         }
         mbar_init(&tfull[0], 1);
         mbar_init(&tfull[1], 1);
-        mbar_init(&tempty[0], 8);
-        mbar_init(&tempty[1], 8);
+        mbar_init(&tempty[0], 8 * CG);            // the leader's barrier also collects the peer's 8 epilogue warps
+        mbar_init(&tempty[1], 8 * CG);
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc(tmem_slot, 512);   // 2 accumulator stages x 256 fp32 columns
+    if (warp == 1) {                              // 2 accumulator stages x 256 fp32 columns
+        if constexpr (CG == 2) tmem_alloc_2sm(tmem_slot, 512);
+        else tmem_alloc(tmem_slot, 512);
+    }
     tc_fence_before();
-    __syncthreads();
+    if constexpr (CG == 2) cluster_sync_all();    // peer barriers are initialised before any remote arrive / multicast
+    else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const int total_tiles = g.tiles_m * g.tiles_n;
+    // work items: (pair of consecutive M-tiles, N-tile); CTA `rank` of the pair owns M-tile 2*pm + rank
+    const int pairs_m = (g.tiles_m + CG - 1) / CG;
+    const int total_pairs = pairs_m * g.tiles_n;
+    const int first_pair = blockIdx.x / CG;
+    const int pair_stride = gridDim.x / CG;
     const int k_iters = g.ntaps * g.k_chunks;
 
     if (warp == 0) {
@@ -75,9 +86,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int tn = tile % g.tiles_n;
-                int tm = tile / g.tiles_n;
+            for (int pt = first_pair; pt < total_pairs; pt += pair_stride) {
+                const int tn = pt % g.tiles_n;
+                const int tmi = (pt / g.tiles_n) * CG + static_cast<int>(rank);
+                int tm = tmi;
                 int org[GEMM_MAX_RDIMS];
 #pragma unroll
                 for (int d = 0; d < GEMM_MAX_RDIMS; ++d) {
@@ -85,6 +97,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
                     org[d] = (tm % td) * g.box[d];
                     tm /= td;
                 }
+                if (tmi >= g.tiles_m) org[0] = g.dim[0];       // odd tail: this CTA's half is all out of bounds (zeros)
                 const int bbatch = g.b_batch_dim >= 0 ? org[g.b_batch_dim] : 0;
                 for (int tap = 0; tap < g.ntaps; ++tap) {
                     const int c1 = org[0] + g.tap_off[tap][0];
@@ -95,15 +108,28 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
                         mbar_wait(&empty[stage], phase ^ 1u);
                         uint8_t* sa = smem + stage * C::kStageBytes;
                         uint8_t* sb = sa + kABytes;
-                        mbar_expect_tx(&full[stage], static_cast<uint32_t>(g.a_tx_bytes + C::kBBytes));
                         const int k0 = kc * GEMM_BLOCK_K;
-                        switch (g.nd) {
-                            case 1: tma_load_2d(sa, &g.map_a, &full[stage], k0, c1); break;
-                            case 2: tma_load_3d(sa, &g.map_a, &full[stage], k0, c1, c2); break;
-                            case 3: tma_load_4d(sa, &g.map_a, &full[stage], k0, c1, c2, c3); break;
-                            default: tma_load_5d(sa, &g.map_a, &full[stage], k0, c1, c2, c3, c4); break;
+                        if constexpr (CG == 2) {
+                            // both CTAs' bytes complete on the LEADER's barrier; only the leader arms it
+                            if (leader) mbar_expect_tx(&full[stage], static_cast<uint32_t>(2 * (g.a_tx_bytes + C::kBBytes)));
+                            const uint32_t lb = leader_bar_addr(&full[stage]);
+                            switch (g.nd) {
+                                case 1: tma_load_2d_2sm(sa, &g.map_a, lb, k0, c1); break;
+                                case 2: tma_load_3d_2sm(sa, &g.map_a, lb, k0, c1, c2); break;
+                                case 3: tma_load_4d_2sm(sa, &g.map_a, lb, k0, c1, c2, c3); break;
+                                default: tma_load_5d_2sm(sa, &g.map_a, lb, k0, c1, c2, c3, c4); break;
+                            }
+                            tma_load_3d_2sm(sb, &g.map_b, lb, k0, tn * BN + static_cast<int>(rank) * (BN / 2), tap + bbatch);
+                        } else {
+                            mbar_expect_tx(&full[stage], static_cast<uint32_t>(g.a_tx_bytes + C::kBBytes));
+                            switch (g.nd) {
+                                case 1: tma_load_2d(sa, &g.map_a, &full[stage], k0, c1); break;
+                                case 2: tma_load_3d(sa, &g.map_a, &full[stage], k0, c1, c2); break;
+                                case 3: tma_load_4d(sa, &g.map_a, &full[stage], k0, c1, c2, c3); break;
+                                default: tma_load_5d(sa, &g.map_a, &full[stage], k0, c1, c2, c3, c4); break;
+                            }
+                            tma_load_3d(sb, &g.map_b, &full[stage], k0, tn * BN, tap + bbatch);
                         }
-                        tma_load_3d(sb, &g.map_b, &full[stage], k0, tn * BN, tap + bbatch);
                         if (++stage == C::kStages) {
                             stage = 0;
                             phase ^= 1u;
@@ -113,14 +139,15 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
             }
         }
     } else if (warp == 1) {
-        // ------------------------------------------------------------------ MMA issuer
-        constexpr uint32_t idesc = umma_idesc_f16(GEMM_BLOCK_M, BN);
+        // ------------------------------------------------------------------ MMA issuer (pair leader only)
+        constexpr uint32_t idesc = umma_idesc_f16(GEMM_BLOCK_M * CG, BN);
+        if (leader) {
         int stage = 0;
         uint32_t phase = 0;
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            mbar_wait(&tempty[acc], acc_phase ^ 1u);      // epilogue has drained this accumulator stage
+        for (int pt = first_pair; pt < total_pairs; pt += pair_stride) {
+            mbar_wait(&tempty[acc], acc_phase ^ 1u);      // epilogue(s) have drained this accumulator stage
             tc_fence_after();
             const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * 256);
             for (int it = 0; it < k_iters; ++it) {
@@ -133,11 +160,20 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
 #pragma unroll
                     for (int k = 0; k < GEMM_BLOCK_K / 16; ++k) {
                         // +32 B per K=16 step: start-address field is in 16 B units
-                        umma_f16(tmem_d, da + static_cast<uint64_t>(k * 2), db + static_cast<uint64_t>(k * 2), idesc,
-                                 (it | k) != 0 ? 1u : 0u);
+                        if constexpr (CG == 2)
+                            umma_f16_2sm(tmem_d, da + static_cast<uint64_t>(k * 2), db + static_cast<uint64_t>(k * 2), idesc,
+                                         (it | k) != 0 ? 1u : 0u);
+                        else
+                            umma_f16(tmem_d, da + static_cast<uint64_t>(k * 2), db + static_cast<uint64_t>(k * 2), idesc,
+                                     (it | k) != 0 ? 1u : 0u);
                     }
-                    umma_commit(&empty[stage]);                       // smem stage reusable once these MMAs retire
-                    if (it == k_iters - 1) umma_commit(&tfull[acc]);  // accumulator complete
+                    if constexpr (CG == 2) {
+                        umma_commit_2sm(&empty[stage]);                       // frees the stage in BOTH CTAs
+                        if (it == k_iters - 1) umma_commit_2sm(&tfull[acc]);  // both epilogues may drain their half
+                    } else {
+                        umma_commit(&empty[stage]);                       // smem stage reusable once these MMAs retire
+                        if (it == k_iters - 1) umma_commit(&tfull[acc]);  // accumulator complete
+                    }
                 }
                 __syncwarp();
                 if (++stage == C::kStages) {
@@ -148,6 +184,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1u;
         }
+        }   // leader
     } else {
         // ------------------------------------------------------------------ epilogue (warps 2..9)
         // 8 warps: TMEM lane quadrant q = warp & 3 (a warp may only touch lanes 32q..32q+31), column chunks are
@@ -168,13 +205,14 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         const bool vec_ok = ((g.ldo & 7) == 0) && ((g.N & 7) == 0) && (!geglu || (g.N & 15) == 0) &&
                             (g.residual == nullptr || (g.ldr & 7) == 0);
         const bool bias_vec = (g.bias != nullptr) && ((g.N & 7) == 0) && ((g.bias_stride & 7) == 0);
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            const int tn = tile % g.tiles_n;
-            int tm = tile / g.tiles_n;
+        for (int pt = first_pair; pt < total_pairs; pt += pair_stride) {
+            const int tn = pt % g.tiles_n;
+            const int tmi = (pt / g.tiles_n) * CG + static_cast<int>(rank);
+            int tm = tmi;
             // tile row r -> global row
             long long grow = 0;
             long long mul = 1;
-            bool valid = true;
+            bool valid = tmi < g.tiles_m;
             {
                 int rr = r;
 #pragma unroll
@@ -323,17 +361,22 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[acc]);
+            if (lane == 0) {
+                if (CG == 2 && !leader) mbar_arrive_cluster(&tempty[acc], 0);   // the MMA issuer lives in the leader CTA
+                else mbar_arrive(&tempty[acc]);
+            }
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1u;
         }
     }
 
     tc_fence_before();
-    __syncthreads();
+    if constexpr (CG == 2) cluster_sync_all();    // no CTA may exit (or free TMEM) while its peer can still signal it
+    else __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, 512);
+        if constexpr (CG == 2) tmem_dealloc_2sm(tmem_base, 512);
+        else tmem_dealloc(tmem_base, 512);
     }
 }
 
@@ -360,14 +403,31 @@ int encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dim
     return 0;
 }
 
-template <int BN>
-int set_attr() {
-    if (cudaFuncSetAttribute(gemm_tc_kernel<BN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             Cfg<BN>::kSmemBytes) != cudaSuccess) return -1;
-    if (BN >= 64 && BN != 160)
-        if (cudaFuncSetAttribute(gemm_tc_kernel<(BN >= 64 && BN != 160) ? BN : 64, true>,
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::kSmemBytes) != cudaSuccess) return -1;
-    return 0;
+// ---- (BN, GEGLU, CG) dispatch table
+struct Variant {
+    int bn, geglu, cg, smem;
+    const void* fn;
+};
+template <int BN, bool G, int CG>
+Variant variant() {
+    return Variant{BN, G ? 1 : 0, CG, Cfg<BN, CG>::kSmemBytes, reinterpret_cast<const void*>(&gemm_tc_kernel<BN, G, CG>)};
+}
+const Variant* variants(int* n) {
+    static const Variant v[] = {
+        variant<16, false, 1>(),  variant<64, false, 1>(),  variant<128, false, 1>(), variant<160, false, 1>(),
+        variant<256, false, 1>(), variant<64, true, 1>(),   variant<128, true, 1>(),  variant<256, true, 1>(),
+        variant<64, false, 2>(),  variant<128, false, 2>(), variant<160, false, 2>(), variant<256, false, 2>(),
+        variant<64, true, 2>(),   variant<128, true, 2>(),  variant<256, true, 2>(),
+    };
+    *n = static_cast<int>(sizeof(v) / sizeof(v[0]));
+    return v;
+}
+const Variant* find_variant(int bn, bool geglu, int cg) {
+    int n;
+    const Variant* v = variants(&n);
+    for (int i = 0; i < n; ++i)
+        if (v[i].bn == bn && v[i].geglu == (geglu ? 1 : 0) && v[i].cg == cg) return &v[i];
+    return nullptr;
 }
 
 }  // namespace
@@ -382,7 +442,12 @@ int gemm_init() {
         return -1;
     }
     g_encode = reinterpret_cast<EncodeTiledFn>(fn);
-    if (set_attr<16>() || set_attr<64>() || set_attr<128>() || set_attr<160>() || set_attr<256>()) {
+    int nv = 0;
+    const Variant* vs = variants(&nv);
+    bool attr_fail = false;
+    for (int i = 0; i < nv; ++i)
+        if (cudaFuncSetAttribute(vs[i].fn, cudaFuncAttributeMaxDynamicSharedMemorySize, vs[i].smem) != cudaSuccess) attr_fail = true;
+    if (attr_fail) {
         fprintf(stderr, "[t2v_b200] cudaFuncSetAttribute(max dynamic smem) failed: %s\n",
                 cudaGetErrorString(cudaGetLastError()));
         return -1;
@@ -473,6 +538,10 @@ int gemm_plan(const GemmProblem& p, GemmPlan* plan, int num_sms) {
         }
     }
     plan->bn = bn;
+    // CTA pairs (cta_group::2) whenever there are at least two M-tiles: halves the B-operand L2/smem traffic
+    static const bool no_pairs = getenv("T2V_NO_2CTA") != nullptr;
+    plan->cg = p.force_cg ? p.force_cg : ((g.tiles_m >= 2 && bn >= 64 && !no_pairs) ? 2 : 1);
+    if (bn < 64 || p.b_batch_dim >= 0) plan->cg = 1;     // a pair shares ONE B tile: never across B batches
     g.tiles_n = (p.N + bn - 1) / bn;
     if ((p.flags & GEMM_GEGLU) && (p.N % bn) != 0) {
         fprintf(stderr, "[t2v_b200] gemm_plan: GEGLU needs N %% BN == 0 (N %d BN %d)\n", p.N, bn);
@@ -500,43 +569,38 @@ int gemm_plan(const GemmProblem& p, GemmPlan* plan, int num_sms) {
                               static_cast<cuuint64_t>(nb)};
         const cuuint64_t ldb = static_cast<cuuint64_t>(p.ldb > 0 ? p.ldb : p.K);
         cuuint64_t strides[2] = {ldb * 2, ldb * 2 * static_cast<cuuint64_t>(p.n_alloc)};
-        cuuint32_t box[3] = {GEMM_BLOCK_K, static_cast<cuuint32_t>(bn), 1};
+        cuuint32_t box[3] = {GEMM_BLOCK_K, static_cast<cuuint32_t>(bn / plan->cg), 1};   // a CTA of a pair stages half of B
         if (encode_map(&g.map_b, p.b, 3, dims, strides, box) != 0) return -6;
     }
-    const long long total = static_cast<long long>(g.tiles_m) * g.tiles_n;
-    plan->grid = static_cast<int>(std::min<long long>(total, num_sms));
-    switch (bn) {
-        case 16: plan->smem = Cfg<16>::kSmemBytes; break;
-        case 64: plan->smem = Cfg<64>::kSmemBytes; break;
-        case 128: plan->smem = Cfg<128>::kSmemBytes; break;
-        case 160: plan->smem = Cfg<160>::kSmemBytes; break;
-        case 256: plan->smem = Cfg<256>::kSmemBytes; break;
-        default: return -7;
-    }
+    const Variant* var = find_variant(bn, (p.flags & GEMM_GEGLU) != 0, plan->cg);
+    if (var == nullptr) return -7;
+    const long long pairs = static_cast<long long>((g.tiles_m + plan->cg - 1) / plan->cg) * g.tiles_n;
+    plan->grid = plan->cg * static_cast<int>(std::min<long long>(pairs, num_sms / plan->cg));
+    plan->smem = var->smem;
     plan->flops = 2.0 * static_cast<double>(rows) * p.N * p.K * p.ntaps;
     return 0;
 }
 
 int gemm_launch(const GemmPlan& plan, cudaStream_t stream) {
-    const bool geglu = (plan.desc.flags & GEMM_GEGLU) != 0;
-    if (geglu) {
-        switch (plan.bn) {
-            case 64: gemm_tc_kernel<64, true><<<plan.grid, kThreads, plan.smem, stream>>>(plan.desc); break;
-            case 128: gemm_tc_kernel<128, true><<<plan.grid, kThreads, plan.smem, stream>>>(plan.desc); break;
-            case 256: gemm_tc_kernel<256, true><<<plan.grid, kThreads, plan.smem, stream>>>(plan.desc); break;
-            default: return -1;
-        }
-    } else {
-        switch (plan.bn) {
-            case 16: gemm_tc_kernel<16, false><<<plan.grid, kThreads, plan.smem, stream>>>(plan.desc); break;
-            case 64: gemm_tc_kernel<64, false><<<plan.grid, kThreads, plan.smem, stream>>>(plan.desc); break;
-            case 128: gemm_tc_kernel<128, false><<<plan.grid, kThreads, plan.smem, stream>>>(plan.desc); break;
-            case 160: gemm_tc_kernel<160, false><<<plan.grid, kThreads, plan.smem, stream>>>(plan.desc); break;
-            case 256: gemm_tc_kernel<256, false><<<plan.grid, kThreads, plan.smem, stream>>>(plan.desc); break;
-            default: return -1;
-        }
+    const Variant* var = find_variant(plan.bn, (plan.desc.flags & GEMM_GEGLU) != 0, plan.cg);
+    if (var == nullptr) return -1;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(static_cast<unsigned>(plan.grid));
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = static_cast<size_t>(plan.smem);
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    if (plan.cg == 2) {
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
     }
-    return cudaGetLastError() == cudaSuccess ? 0 : -2;
+    void* args[1] = {const_cast<GemmDesc*>(&plan.desc)};
+    return cudaLaunchKernelExC(&cfg, var->fn, args) == cudaSuccess ? 0 : -2;
 }
 
 }  // namespace t2v

@@ -72,11 +72,13 @@ struct GemmProblem {
     long long ldr;
     float alpha;
     int force_bn;                    // 0 = auto
+    int force_cg;                    // 0 = auto, 1 / 2
 };
 
 struct GemmPlan {
     GemmDesc desc;
     int bn;
+    int cg;                          // 1 = one CTA per tile, 2 = CTA pair (tcgen05 cta_group::2) per two M-tiles
     int grid;
     int smem;
     double flops;

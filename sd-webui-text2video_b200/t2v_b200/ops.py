@@ -18,7 +18,7 @@ def _ia(vals):
 
 
 def gemm(a, w_packed, N, *, K=None, lda=None, dims=None, taps=None, n_alloc=None, b_batch_dim=-1, flags=0, out=None,
-         ldo=None, bias=None, bias_rows=0, bias_stride=0, residual=None, ldr=None, alpha=1.0, force_bn=0):
+         ldo=None, bias=None, bias_rows=0, bias_stride=0, residual=None, ldr=None, alpha=1.0, force_bn=0, force_cg=0):
     """out[row, n] = alpha * sum_tap sum_k a[row + tap, k] w[tap, n, k] (+bias) (+residual)."""
     l = _lib.lib()
     rows = a.shape[0]
@@ -36,7 +36,7 @@ def gemm(a, w_packed, N, *, K=None, lda=None, dims=None, taps=None, n_alloc=None
     ldr = ldr if ldr is not None else (residual.stride(0) if residual is not None else 0)
     rc = l.t2v_op_gemm(_lib.ptr(a), lda, K, nd, _ia(dims), len(taps), _ia(flat), _lib.ptr(w_packed), n_alloc, N,
                        b_batch_dim, flags, _lib.ptr(out), ldo, _lib.ptr(bias), bias_rows, bias_stride,
-                       _lib.ptr(residual), ldr, alpha, force_bn, _lib.stream_ptr())
+                       _lib.ptr(residual), ldr, alpha, force_bn, force_cg, _lib.stream_ptr())
     _lib.check(rc, 'op_gemm')
     return out
 

@@ -19,12 +19,15 @@ def ops():
     return o
 
 
+@pytest.mark.parametrize('cg', [1, 2])
 @pytest.mark.parametrize('M,K,N,bn,bias,res', [
     (128, 64, 64, 64, True, False), (256, 128, 128, 128, False, False), (1000, 320, 320, 0, True, False),
     (1000, 320, 320, 160, True, True), (4096, 512, 256, 256, True, False), (24576, 320, 2560, 0, True, False),
     (384, 1280, 1280, 0, True, True), (77, 1024, 640, 0, False, False), (512, 320, 4, 16, True, False),
     (1, 64, 64, 0, True, False), (129, 72, 200, 0, True, True)])
-def test_linear(ops, M, K, N, bn, bias, res):
+def test_linear(ops, M, K, N, bn, bias, res, cg):
+    if cg == 2 and (bn == 16 or N <= 16):
+        pytest.skip('CTA pairs need BN >= 64')
     a = torch.randn(M, K, device=dev).half()
     w = (torch.randn(N, K, device=dev) / K ** 0.5).half()
     b = torch.randn(N, device=dev).half() if bias else None
@@ -32,7 +35,7 @@ def test_linear(ops, M, K, N, bn, bias, res):
     n_alloc = max(N, 16)
     wp = torch.zeros(1, n_alloc, K, device=dev, dtype=torch.half)
     wp[0, :N] = w
-    out = ops.gemm(a, wp, N, n_alloc=n_alloc, bias=b, residual=r, force_bn=bn)
+    out = ops.gemm(a, wp, N, n_alloc=n_alloc, bias=b, residual=r, force_bn=bn, force_cg=cg)
     ref = a.float() @ w.float().t()
     if bias:
         ref = ref + b.float()
@@ -45,36 +48,41 @@ def test_linear(ops, M, K, N, bn, bias, res):
                                              (4, 4, 4, 256, 128), (5, 2, 2, 64, 64), (2, 16, 8, 64, 128),
                                              (2, 18, 32, 64, 64), (2, 9, 16, 64, 64), (3, 16, 16, 8, 64),
                                              (3, 16, 16, 320, 4), (1, 1, 1, 64, 64), (2, 6, 200, 64, 64)])
-def test_conv3x3_implicit_gemm(ops, NF, h, w, Cin, Cout):
+@pytest.mark.parametrize('cg', [1, 2])
+def test_conv3x3_implicit_gemm(ops, NF, h, w, Cin, Cout, cg):
+    if cg == 2 and Cout < 64:
+        pytest.skip('CTA pairs need BN >= 64')
     x = torch.randn(NF, h, w, Cin, device=dev).half()
     wt = (torch.randn(Cout, Cin, 3, 3, device=dev) / (9 * Cin) ** 0.5).half()
     b = torch.randn(Cout, device=dev).half()
     n_alloc = max(Cout, 16)
     wp = ops.pack_conv_weight(wt, n_alloc=n_alloc)
-    out = ops.gemm(x.view(-1, Cin), wp, Cout, dims=[w, h, NF], taps=ops.conv_taps_2d(), n_alloc=n_alloc, bias=b)
+    out = ops.gemm(x.view(-1, Cin), wp, Cout, dims=[w, h, NF], taps=ops.conv_taps_2d(), n_alloc=n_alloc, bias=b, force_cg=cg)
     ref = F.conv2d(x.permute(0, 3, 1, 2).float(), wt.float(), b.float(), padding=1).permute(0, 2, 3, 1).reshape(-1, Cout)
     assert rel(out, ref) < 2e-3
 
 
 @pytest.mark.parametrize('B,Fr,P,C', [(1, 24, 256, 320), (2, 4, 16, 128), (2, 5, 4, 64), (1, 3, 128, 64), (2, 1, 64, 64)])
-def test_temporal_conv(ops, B, Fr, P, C):
+@pytest.mark.parametrize('cg', [1, 2])
+def test_temporal_conv(ops, B, Fr, P, C, cg):
     x = torch.randn(B, Fr, P, C, device=dev).half()
     wt = (torch.randn(C, C, 3, 1, 1, device=dev) / (3 * C) ** 0.5).half()
     b = torch.randn(C, device=dev).half()
     out = ops.gemm(x.view(-1, C), ops.pack_conv_weight(wt), C, dims=[P, Fr, B], taps=ops.conv_taps_temporal(), bias=b,
-                   residual=x.view(-1, C))
+                   residual=x.view(-1, C), force_cg=cg)
     x5 = x.permute(0, 3, 1, 2).reshape(B, C, Fr, P, 1).float()
     ref = (F.conv3d(x5, wt.float(), b.float(), padding=(1, 0, 0)) + x5).reshape(B, C, Fr, P).permute(0, 2, 3, 1).reshape(-1, C)
     assert rel(out, ref) < 2e-3
 
 
 @pytest.mark.parametrize('M,K,H,bn', [(1024, 320, 1280, 256), (512, 64, 256, 128), (300, 64, 256, 64)])
-def test_geglu_epilogue(ops, M, K, H, bn):
+@pytest.mark.parametrize('cg', [1, 2])
+def test_geglu_epilogue(ops, M, K, H, bn, cg):
     a = torch.randn(M, K, device=dev).half()
     w = (torch.randn(2 * H, K, device=dev) / K ** 0.5).half()
     b = torch.randn(2 * H, device=dev).half()
     wp, bp = ops.pack_geglu_weight(w, b, bn)
-    out = ops.gemm(a, wp, 2 * H, bias=bp, flags=ops.GEMM_GEGLU, force_bn=bn)
+    out = ops.gemm(a, wp, 2 * H, bias=bp, flags=ops.GEMM_GEGLU, force_bn=bn, force_cg=cg)
     hh = (a.float() @ w.float().t() + b.float()).half()
     xa, gate = hh.chunk(2, dim=-1)
     ref = xa * F.gelu(gate)
