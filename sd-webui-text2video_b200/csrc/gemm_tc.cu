@@ -28,7 +28,7 @@ struct Cfg {
     static constexpr int kBBytes = (BN / CG) * GEMM_BLOCK_K * 2;      // a CTA of a pair stages half of the B tile
     static constexpr int kStageBytes = kABytes + kBBytes;
     static constexpr int kStages = (kSmemBudget / kStageBytes) > 8 ? 8 : (kSmemBudget / kStageBytes);
-    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + 2048 /*bias tiles*/;
 };
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
@@ -47,6 +47,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     uint64_t* tfull = bars + 2 * C::kStages;     // [2] MMA -> epilogue
     uint64_t* tempty = tfull + 2;                // [2] epilogue -> MMA
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    float* bias_s = reinterpret_cast<float*>(bars) + 64;         // [2 accumulator stages][256] fp32 bias tile (256 B after the barriers)
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -204,7 +205,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         const int nvalid = geglu ? g.N / 2 : g.N;
         const bool vec_ok = ((g.ldo & 7) == 0) && ((g.N & 7) == 0) && (!geglu || (g.N & 15) == 0) &&
                             (g.residual == nullptr || (g.ldr & 7) == 0);
-        const bool bias_vec = (g.bias != nullptr) && ((g.N & 7) == 0) && ((g.bias_stride & 7) == 0);
+        // A bias shared by all rows is staged once per tile in smem (its L2 latency hides behind the wait for the
+        // accumulator); per-sample bias rows (time-embedding add of the ResBlock convs) are read per thread.
+        const bool bias_staged = (g.bias != nullptr) && (g.bias_rows == 0);
+        const int et = static_cast<int>(threadIdx.x) - 64;       // 0..255 among the epilogue threads
         for (int pt = first_pair; pt < total_pairs; pt += pair_stride) {
             const int tn = pt % g.tiles_n;
             const int tmi = (pt / g.tiles_n) * CG + static_cast<int>(rank);
@@ -245,9 +249,19 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
                 }
             };
             if (hsel < nchunks) prefetch_res(hsel);
+            float bstage = 0.f;
+            if (bias_staged && et < BN) {
+                const int col = tn * BN + et;
+                if (col < g.N) bstage = __half2float(__ldg(g.bias + col));
+            }
 
             mbar_wait(&tfull[acc], acc_phase);
             tc_fence_after();
+            const float* bs = bias_s + acc * 256;
+            if (bias_staged) {
+                if (et < BN) bias_s[acc * 256 + et] = bstage;
+                asm volatile("bar.sync 1, 256;" ::: "memory");     // epilogue warps only (named barrier 1)
+            }
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * 256);
             for (int ci = hsel; ci < nchunks; ci += 2) {
                 const int c0 = ci * CW;
@@ -265,28 +279,14 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
                 if (ci + 2 < nchunks) prefetch_res(ci + 2);
                 const int pcol = tn * BN + c0;                    // packed (accumulator) column of v[0]
                 float bv[CW], bg[CW];
-                if (bias_vec) {
+                if (bias_staged) {
 #pragma unroll
-                    for (int k = 0; k < NV; ++k) {
-                        uint4 t4 = make_uint4(0, 0, 0, 0);
-                        if (pcol + k * 8 < g.N) t4 = __ldg(reinterpret_cast<const uint4*>(bias + pcol + k * 8));
-                        const __half2* h2 = reinterpret_cast<const __half2*>(&t4);
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const float2 f = __half22float2(h2[e]);
-                            bv[k * 8 + 2 * e] = f.x;
-                            bv[k * 8 + 2 * e + 1] = f.y;
-                        }
+                    for (int j = 0; j < CW; j += 4) {
+                        const float4 t4 = *reinterpret_cast<const float4*>(bs + c0 + j);       // smem broadcast
+                        bv[j] = t4.x; bv[j + 1] = t4.y; bv[j + 2] = t4.z; bv[j + 3] = t4.w;
                         if (geglu) {
-                            uint4 g4 = make_uint4(0, 0, 0, 0);
-                            if (pcol + BN / 2 + k * 8 < g.N) g4 = __ldg(reinterpret_cast<const uint4*>(bias + pcol + BN / 2 + k * 8));
-                            const __half2* gh2 = reinterpret_cast<const __half2*>(&g4);
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                const float2 f = __half22float2(gh2[e]);
-                                bg[k * 8 + 2 * e] = f.x;
-                                bg[k * 8 + 2 * e + 1] = f.y;
-                            }
+                            const float4 g4 = *reinterpret_cast<const float4*>(bs + BN / 2 + c0 + j);
+                            bg[j] = g4.x; bg[j + 1] = g4.y; bg[j + 2] = g4.z; bg[j + 3] = g4.w;
                         }
                     }
                 } else {
@@ -538,9 +538,11 @@ int gemm_plan(const GemmProblem& p, GemmPlan* plan, int num_sms) {
         }
     }
     plan->bn = bn;
-    // CTA pairs (cta_group::2) whenever there are at least two M-tiles: halves the B-operand L2/smem traffic
-    static const bool no_pairs = getenv("T2V_NO_2CTA") != nullptr;
-    plan->cg = p.force_cg ? p.force_cg : ((g.tiles_m >= 2 && bn >= 64 && !no_pairs) ? 2 : 1);
+    // CTA pairs (cta_group::2, M = 256 per pair, each CTA stages half of B).  Measured on B200 (profiles/r01_ncu_gemm.md):
+    // no gain over one CTA per tile for this kernel's shapes (69 % vs 66 % tensor-pipe at 24576x2560x1280, slightly slower
+    // on the K = 320 layers), so pairs are opt-in (T2V_2CTA=1 or force_cg) until the pair path gets TMA multicast.
+    static const bool use_pairs = getenv("T2V_2CTA") != nullptr;
+    plan->cg = p.force_cg ? p.force_cg : ((g.tiles_m >= 2 && bn >= 64 && use_pairs) ? 2 : 1);
     if (bn < 64 || p.b_batch_dim >= 0) plan->cg = 1;     // a pair shares ONE B tile: never across B batches
     g.tiles_n = (p.N + bn - 1) / bn;
     if ((p.flags & GEMM_GEGLU) && (p.N % bn) != 0) {

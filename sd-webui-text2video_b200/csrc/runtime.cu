@@ -464,10 +464,12 @@ Tok group_norm(NetCtx& c, const Tok& x, const std::string& prefix, long long row
     void* ws = c.gn_ws;
     const int sms = c.b->sms();
     const Tok xx = x;
+    char lab[96];
+    snprintf(lab, sizeof(lab), "groupnorm rows=%lld C=%d inst_rows=%lld", x.rows, x.C, rows_per_inst);
     c.b->step([=](cudaStream_t s) {
         return groupnorm_silu(xx.p, xx.ld, y.p, y.ld, xx.rows, xx.C, static_cast<int>(rows_per_inst), g, bt, eps, silu ? 1 : 0,
                               ws, sms, s);
-    }, 2, STEP_NORM, 0.0, "groupnorm");
+    }, 2, STEP_NORM, 0.0, lab);
     return y;
 }
 
@@ -476,7 +478,9 @@ Tok layer_norm(NetCtx& c, const Tok& x, const std::string& prefix) {
     const __half* g = prm(c, prefix + ".weight");
     const __half* bt = prm(c, prefix + ".bias");
     const Tok xx = x;
-    c.b->step([=](cudaStream_t s) { return layernorm(xx.p, xx.ld, y.p, y.ld, xx.rows, xx.C, g, bt, 1e-5f, s); }, 1, STEP_NORM, 0.0, "layernorm");
+    char lab[96];
+    snprintf(lab, sizeof(lab), "layernorm rows=%lld C=%d", x.rows, x.C);
+    c.b->step([=](cudaStream_t s) { return layernorm(xx.p, xx.ld, y.p, y.ld, xx.rows, xx.C, g, bt, 1e-5f, s); }, 1, STEP_NORM, 0.0, lab);
     return y;
 }
 
