@@ -23,6 +23,10 @@ constexpr int GEMM_MAX_RDIMS = 4;
 enum GemmFlags : int {
     GEMM_GEGLU = 1,        // epilogue: out[:, j] = (acc[:, j] + b) * gelu(acc[:, BN/2 + j] + b)  (weights interleaved per tile)
     GEMM_OUT_F32 = 2,      // store fp32 instead of fp16
+    // bring-up / performance-isolation switches (never set by the model code)
+    GEMM_DBG_NO_STORE = 256,   // epilogue skips the global stores
+    GEMM_DBG_NO_EPI = 512,     // epilogue releases the accumulator without reading it
+    GEMM_DBG_NO_MMA = 1024,    // MMA warp commits without issuing tcgen05.mma (pure TMA pipeline)
 };
 
 struct GemmDesc {

@@ -11,7 +11,7 @@ namespace t2v {
 size_t gn_workspace_bytes(int rows_per_inst, int n_inst, int num_sms);
 int groupnorm_silu(const __half* x, long long ldx, __half* y, long long ldy, long long rows, int C, int rows_per_inst,
                    const __half* gamma, const __half* beta, float eps, int silu, void* workspace, int num_sms,
-                   cudaStream_t stream);
+                   cudaStream_t stream, int phase = 0);   // phase 0: stats + apply, 1: stats only, 2: apply only
 int layernorm(const __half* x, long long ldx, __half* y, long long ldy, long long rows, int C, const __half* gamma,
               const __half* beta, float eps, cudaStream_t stream);
 

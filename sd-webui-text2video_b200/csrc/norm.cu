@@ -96,12 +96,28 @@ __global__ void __launch_bounds__(kStatsThreads) gn_stats_kernel(const __half* _
     __syncthreads();
     if (is_last) {
         __threadfence();
-        if (threadIdx.x < kGroups) {
+        // fold the chunk partials: 8 thread-parts per group read strided chunks (independent L2 loads in flight), then a
+        // fixed-order combine -> deterministic and no serial chain of nchunks dependent loads
+        __shared__ double fold[8][kGroups][2];
+        {
+            const int gidx = threadIdx.x & 31, part = threadIdx.x >> 5;
             double a = 0.0, b = 0.0;
-            for (int ch = 0; ch < nchunks; ++ch) {
-                const float2 p = __ldcg(&partial[(static_cast<long long>(inst) * nchunks + ch) * kGroups + threadIdx.x]);
+#pragma unroll 4
+            for (int ch = part; ch < nchunks; ch += 8) {
+                const float2 p = __ldcg(&partial[(static_cast<long long>(inst) * nchunks + ch) * kGroups + gidx]);
                 a += p.x;
                 b += p.y;
+            }
+            fold[part][gidx][0] = a;
+            fold[part][gidx][1] = b;
+        }
+        __syncthreads();
+        if (threadIdx.x < kGroups) {
+            double a = 0.0, b = 0.0;
+#pragma unroll
+            for (int part = 0; part < 8; ++part) {
+                a += fold[part][threadIdx.x][0];
+                b += fold[part][threadIdx.x][1];
             }
             const double n = static_cast<double>(rows_per_inst) * cpg;
             const double mean = a / n;
@@ -255,7 +271,7 @@ size_t gn_workspace_bytes(int rows_per_inst, int n_inst, int num_sms) {
 
 int groupnorm_silu(const __half* x, long long ldx, __half* y, long long ldy, long long rows, int C, int rows_per_inst,
                    const __half* gamma, const __half* beta, float eps, int silu, void* workspace, int num_sms,
-                   cudaStream_t stream) {
+                   cudaStream_t stream, int phase) {
     if (C % 32 != 0 || C % 8 != 0 || rows % rows_per_inst != 0) return -1;
     const int n_inst = static_cast<int>(rows / rows_per_inst);
     const int rpc = gn_rows_per_chunk(rows_per_inst, n_inst, num_sms);
@@ -265,8 +281,10 @@ int groupnorm_silu(const __half* x, long long ldx, __half* y, long long ldy, lon
     unsigned int* counters = reinterpret_cast<unsigned int*>(ws);
     float2* stats = reinterpret_cast<float2*>(ws + kCounterBytes);
     float2* partial = stats + static_cast<size_t>(n_inst) * kGroups;
-    gn_stats_kernel<<<dim3(nchunks, n_inst), kStatsThreads, 2 * C * sizeof(float), stream>>>(
-        x, ldx, C, rows_per_inst, rpc, nchunks, eps, partial, counters, stats);
+    if (phase != 2)
+        gn_stats_kernel<<<dim3(nchunks, n_inst), kStatsThreads, 2 * C * sizeof(float), stream>>>(
+            x, ldx, C, rows_per_inst, rpc, nchunks, eps, partial, counters, stats);
+    if (phase == 1) return cudaGetLastError() == cudaSuccess ? 0 : -2;
     // rows per apply block: ~8 blocks per SM overall, at least 4 rows
     long long want_blocks = static_cast<long long>(num_sms) * 8;
     long long per_inst = (want_blocks + n_inst - 1) / n_inst;

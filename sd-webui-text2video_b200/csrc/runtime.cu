@@ -465,11 +465,16 @@ Tok group_norm(NetCtx& c, const Tok& x, const std::string& prefix, long long row
     const int sms = c.b->sms();
     const Tok xx = x;
     char lab[96];
-    snprintf(lab, sizeof(lab), "groupnorm rows=%lld C=%d inst_rows=%lld", x.rows, x.C, rows_per_inst);
+    snprintf(lab, sizeof(lab), "gn_stats rows=%lld C=%d inst_rows=%lld", x.rows, x.C, rows_per_inst);
     c.b->step([=](cudaStream_t s) {
         return groupnorm_silu(xx.p, xx.ld, y.p, y.ld, xx.rows, xx.C, static_cast<int>(rows_per_inst), g, bt, eps, silu ? 1 : 0,
-                              ws, sms, s);
-    }, 2, STEP_NORM, 0.0, lab);
+                              ws, sms, s, 1);
+    }, 1, STEP_NORM, 0.0, lab);
+    snprintf(lab, sizeof(lab), "gn_apply rows=%lld C=%d inst_rows=%lld", x.rows, x.C, rows_per_inst);
+    c.b->step([=](cudaStream_t s) {
+        return groupnorm_silu(xx.p, xx.ld, y.p, y.ld, xx.rows, xx.C, static_cast<int>(rows_per_inst), g, bt, eps, silu ? 1 : 0,
+                              ws, sms, s, 2);
+    }, 1, STEP_NORM, 0.0, lab);
     return y;
 }
 
