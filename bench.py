@@ -93,7 +93,9 @@ def cpu_reference_sample(args, nsteps=1, threads=None):
     resolution plus the VAE decode of one frame, scaled to the metric:
         frames/s = F_s / (denoise_steps * t_step + F_s * t_vae_frame)."""
     from oracle import unet_oracle as UO, vae_oracle as VO, samplers_oracle as SO
-    threads = threads or os.cpu_count()
+    # torch's CPU kernels scale poorly past ~16 threads on these small tensors (measured: 128 threads on the GPU box's
+    # host were 50x SLOWER than 8 threads here), so the baseline uses min(cores, 16) threads and reports that number
+    threads = threads or min(os.cpu_count() or 1, 16)
     torch.set_num_threads(threads)
     Fs, h, w = 2, args.height // 8, args.width // 8
     cfg = UO.UNetConfig()

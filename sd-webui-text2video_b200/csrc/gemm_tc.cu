@@ -31,19 +31,7 @@ struct Cfg {
     static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + 2048 /*bias tiles*/;
 };
 
-// erf-form GELU x * Phi(x) (the reference's F.gelu default).  Phi via erfc(|x|/sqrt2) = poly(t) * exp(-x^2/2),
-// t = 1 / (1 + p |x|/sqrt2) (Abramowitz-Stegun 7.1.26): 2 MUFU + 7 FMA instead of erff's ~25 instructions -- the GEGLU
-// epilogue is instruction-issue bound at K = 320.  |error| <= 5e-7 absolute before the fp16 rounding the reference applies.
-__device__ __forceinline__ float gelu_erf(float x) {
-    const float ax = fabsf(x) * 0.70710678118654752440f;
-    const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
-    float p = fmaf(t, 1.061405429f, -1.453152027f);
-    p = fmaf(p, t, 1.421413741f);
-    p = fmaf(p, t, -0.284496736f);
-    p = fmaf(p, t, 0.254829592f);
-    const float half_erfc = 0.5f * p * t * __expf(-ax * ax);
-    return x * (x < 0.f ? half_erfc : 1.0f - half_erfc);
-}
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
 template <int BN, bool GEGLU, int CG>
 __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_constant__ GemmDesc g) {
@@ -219,6 +207,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         const int nvalid = geglu ? g.N / 2 : g.N;
         const bool vec_ok = ((g.ldo & 7) == 0) && ((g.N & 7) == 0) && (!geglu || (g.N & 15) == 0) &&
                             (g.residual == nullptr || (g.ldr & 7) == 0);
+        // 32-byte (one full sector per thread) stores / residual loads when every row segment is 32 B aligned
+        const bool vec32 = vec_ok && !out_f32 && (CW == 32) && ((g.ldo & 15) == 0) && ((nvalid & 15) == 0) &&
+                           ((reinterpret_cast<uintptr_t>(g.out) & 31) == 0) &&
+                           (g.residual == nullptr || (((g.ldr & 15) == 0) && ((reinterpret_cast<uintptr_t>(g.residual) & 31) == 0)));
         // A bias shared by all rows is staged once per tile in smem (its L2 latency hides behind the wait for the
         // accumulator); per-sample bias rows (time-embedding add of the ResBlock convs) are read per thread.
         const bool bias_staged = (g.bias != nullptr) && (g.bias_rows == 0);
@@ -255,10 +247,22 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
             uint4 rnext[NV];
             auto prefetch_res = [&](int ci) {
                 if (res_row != nullptr && vec_ok) {
+                    if (vec32) {
 #pragma unroll
-                    for (int k = 0; k < NV; ++k) {
-                        const int col = ci * CW + k * 8;
-                        if (ocol0 + col < nvalid) rnext[k] = __ldg(reinterpret_cast<const uint4*>(res_row + col));
+                        for (int k = 0; k < NV; k += 2) {
+                            const int col = ci * CW + k * 8;
+                            if (ocol0 + col < nvalid) {
+                                const U32x8 t8 = ldg_256(res_row + col);
+                                rnext[k] = make_uint4(t8.v[0], t8.v[1], t8.v[2], t8.v[3]);
+                                rnext[k + 1] = make_uint4(t8.v[4], t8.v[5], t8.v[6], t8.v[7]);
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < NV; ++k) {
+                            const int col = ci * CW + k * 8;
+                            if (ocol0 + col < nvalid) rnext[k] = __ldg(reinterpret_cast<const uint4*>(res_row + col));
+                        }
                     }
                 }
             };
@@ -355,7 +359,20 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
                             if (ocol + j < nvalid) op[j] = v[j];
                     } else {
                         __half* op = reinterpret_cast<__half*>(g.out) + grow * g.ldo + ocol;
-                        if (vec_ok) {
+                        if (vec32) {
+#pragma unroll
+                            for (int k = 0; k < NV; k += 2) {
+                                if (ocol + k * 8 < nvalid) {
+                                    U32x8 ov;
+#pragma unroll
+                                    for (int e = 0; e < 8; ++e) {
+                                        const __half2 hh = __floats2half2_rn(v[k * 8 + 2 * e], v[k * 8 + 2 * e + 1]);
+                                        ov.v[e] = *reinterpret_cast<const uint32_t*>(&hh);
+                                    }
+                                    stg_256(op + k * 8, ov);
+                                }
+                            }
+                        } else if (vec_ok) {
 #pragma unroll
                             for (int k = 0; k < NV; ++k) {
                                 if (ocol + k * 8 < nvalid) {

@@ -169,6 +169,24 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16])
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// ----------------------------------------------------------------------------- 256-bit global accesses (sm_100+)
+// One 32-byte sector per thread per request: the row-per-thread epilogue is bound by L2 request rate, not bytes.
+struct __align__(32) U32x8 {
+    uint32_t v[8];
+};
+__device__ __forceinline__ U32x8 ldg_256(const void* p) {
+    U32x8 r;
+    asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7])
+                 : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void stg_256(void* p, const U32x8& r) {
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(r.v[0]), "r"(r.v[1]), "r"(r.v[2]),
+                 "r"(r.v[3]), "r"(r.v[4]), "r"(r.v[5]), "r"(r.v[6]), "r"(r.v[7])
+                 : "memory");
+}
+
 // ----------------------------------------------------------------------------- CTA pairs (cta_group::2)
 // Two CTAs of a cluster (ranks 0/1 on the two SMs of a TPC) execute ONE tcgen05.mma of M = 256: each CTA stages its own
 // 128 rows of A and HALF of the B tile; the tensor cores exchange the B halves, so every byte of B is fetched from L2

@@ -1,0 +1,108 @@
+"""GPU: the public entry points end to end (tiny UNet config, full-size VAE, synthetic weights): `process_modelscope`,
+`TextToVideoSynthesis.infer` for the three UI samplers, determinism in the seed, the per-step callback contract, and
+agreement of a short DDIM_Gaussian trajectory + decode with the CPU oracle driven by the same weights."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import unet_oracle as UO, vae_oracle as VO, samplers_oracle as SO
+
+pytestmark = pytest.mark.gpu
+
+TINY = {'unet_dim': 64}
+
+
+@pytest.fixture(scope='module')
+def pipe():
+    from t2v_b200.pipeline import TextToVideoSynthesis
+    cfg = UO.UNetConfig(dim=64)
+    W = UO.make_weights(UO.param_specs(cfg), seed=1)
+    Wv = UO.make_weights(VO.decoder_param_specs(VO.VAEConfig()), seed=3)
+    p = TextToVideoSynthesis(None, model_cfg=TINY, unet_state=W, vae_state=Wv)
+    return p, cfg, W, Wv
+
+
+def conds():
+    g = torch.Generator().manual_seed(2)
+    return torch.randn(1, 77, 1024, generator=g).half(), torch.randn(1, 77, 1024, generator=g).half()
+
+
+@pytest.mark.parametrize('sampler,steps', [('DDIM_Gaussian', 6), ('DDIM', 5), ('UniPC', 5)])
+def test_infer_all_samplers(pipe, sampler, steps):
+    p = pipe[0]
+    c, uc = conds()
+    frames, latent, info = p.infer(c, uc, steps, 3, 123, 7.5, 64, 64, 0.0, 'GPU (half precision)', torch.device('cuda'),
+                                   None, 0, 0.0, None, False, sampler)
+    assert len(frames) == 3 and frames[0].shape == (64, 64, 3) and frames[0].dtype == np.uint8
+    assert latent.shape == (1, 4, 3, 8, 8) and torch.isfinite(latent).all()
+    frames2, latent2, _ = p.infer(c, uc, steps, 3, 123, 7.5, 64, 64, 0.0, 'GPU (half precision)', torch.device('cuda'),
+                                  None, 0, 0.0, None, False, sampler)
+    assert torch.equal(latent, latent2) and all(np.array_equal(a, b) for a, b in zip(frames, frames2))
+    _, latent3, _ = p.infer(c, uc, steps, 3, 124, 7.5, 64, 64, 0.0, 'GPU (half precision)', torch.device('cuda'), None, 0,
+                            0.0, None, False, sampler)
+    assert not torch.equal(latent, latent3)
+    assert 'steps' in info and sampler in info
+
+
+def test_short_trajectory_and_decode_vs_oracle(pipe):
+    p, cfg, W, Wv = pipe
+    c, uc = conds()
+    S, F = 4, 2
+    frames, latent, _ = p.infer(c, uc, S, F, 77, 5.0, 64, 64, 0.0, 'GPU (half precision)', torch.device('cuda'), None, 0,
+                                0.0, None, False, 'DDIM_Gaussian')
+    Wh = {k: v.half().float() for k, v in W.items()}
+    x_T = torch.randn((1, 4, F, 8, 8), generator=torch.Generator('cpu').manual_seed(77))
+    ref = SO.ddim_gaussian_sample(lambda a, b, d: UO.unet_forward(Wh, cfg, a, b, d), SO.linear_sd_betas(), x_T, S,
+                                  c.float(), uc.float(), 5.0)
+    err = (latent.cpu() - ref).abs().max() / ref.abs().max()
+    assert err < 3e-2, err                      # 4 steps x 2 fp16 forwards each, vs fp32 oracle
+    dec = VO.vae_decode({k: v.half().float() for k, v in Wv.items()}, VO.VAEConfig(),
+                        (ref[0].permute(1, 0, 2, 3) / 0.18215))
+    ref_u8 = VO.tensor2vid_u8(dec.permute(1, 0, 2, 3).unsqueeze(0))          # [F, H, W, 3] RGB
+    got = np.stack([f[:, :, ::-1] for f in frames])                             # BGR -> RGB
+    assert np.abs(got.astype(int) - ref_u8.astype(int)).mean() < 3.0
+
+
+def test_callback_and_interrupt(pipe):
+    from t2v_b200 import samplers
+    p = pipe[0]
+    c, uc = conds()
+    samplers.state.interrupted = False
+    calls = []
+    smp = [s for s in samplers.available_samplers if s.name == 'DDIM_Gaussian'][0].init_sampler(
+        p.sd_model, betas=p.diffusion.betas, device=torch.device('cuda'))
+    x = torch.randn(1, 4, 2, 8, 8, device='cuda')
+    smp.sample(S=5, conditioning=c.cuda(), unconditional_conditioning=uc.cuda(), unconditional_guidance_scale=3.0, x_T=x,
+               callback=lambda step: calls.append(step))
+    assert calls == [0, 1, 2, 3, 4]
+
+    class Boom(Exception):
+        pass
+
+    def bad(step):
+        if step == 2:
+            raise Boom()
+    with pytest.raises(Boom):
+        smp.sample(S=5, conditioning=c.cuda(), unconditional_conditioning=uc.cuda(), unconditional_guidance_scale=3.0, x_T=x,
+                   callback=bad)
+    samplers.state.interrupted = True
+    try:
+        with pytest.raises(samplers.InterruptedException):
+            p.infer(c, uc, 4, 2, 1, 3.0, 64, 64, 0.0, 'GPU (half precision)', torch.device('cuda'), None, 0, 0.0, None, False,
+                    'DDIM')
+    finally:
+        samplers.state.interrupted = False
+
+
+def test_process_modelscope_entry_point(pipe):
+    from t2v_b200 import process_modelscope as pm
+    pm.pipe = pipe[0]
+    c, uc = conds()
+    outs = pm.process_modelscope({'prompt_embeds': c, 'n_prompt_embeds': uc, 'steps': 3, 'frames': 2, 'seed': 5, 'cfg_scale': 4.0,
+                                  'width': 64, 'height': 64, 'batch_count': 2, 'sampler': 'DDIM_Gaussian'})
+    assert len(outs) == 2 and len(outs[0]) == 2 and outs[0][0].shape == (64, 64, 3)
+    assert not np.array_equal(outs[0][0], outs[1][0])           # batch i uses seed + i
+    with pytest.raises(RuntimeError):
+        pipe[0].infer('a cat', '', 3, 2, 1, 3.0, 64, 64)        # string prompts need a clip_encoder
+    with pytest.raises(RuntimeError):
+        pipe[0].infer(c, uc, 3, 2, 1, 3.0, 64, 64, 0.0, 'CPU (Low VRAM)')
