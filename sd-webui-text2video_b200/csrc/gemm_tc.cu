@@ -550,7 +550,8 @@ int gemm_plan(const GemmProblem& p, GemmPlan* plan, int num_sms) {
     int bn = p.force_bn;
     if (bn == 0) {
         const int cands[5] = {256, 160, 128, 64, 16};
-        const double eff[5] = {1.0, 0.97, 0.92, 0.70, 0.25};
+        // relative tile efficiency measured on B200 (scripts/gemm_isolate.py): wide tiles move fewer operand bytes per flop
+        const double eff[5] = {1.0, 0.86, 0.80, 0.55, 0.25};
         double best = -1;
         for (int i = 0; i < 5; ++i) {
             const int c = cands[i];
