@@ -155,32 +155,44 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const __half* __restrict_
     const int r1 = min(r0 + rows_per_block, rows_per_inst);
     const long long base_row = static_cast<long long>(inst) * rows_per_inst;
     const int total = (r1 - r0) * C8;
-    for (int i = threadIdx.x; i < total; i += blockDim.x) {
-        const int r = i / C8;
-        const int vc = i - r * C8;
-        const long long row = base_row + r0 + r;
-        const uint4 v = __ldg(reinterpret_cast<const uint4*>(x + row * ldx + vc * 8));
-        const __half* xh = reinterpret_cast<const __half*>(&v);
-        const float4 a0 = *reinterpret_cast<const float4*>(ab + vc * 8);
-        const float4 a1 = *reinterpret_cast<const float4*>(ab + vc * 8 + 4);
-        const float4 b0 = *reinterpret_cast<const float4*>(ab + C + vc * 8);
-        const float4 b1 = *reinterpret_cast<const float4*>(ab + C + vc * 8 + 4);
-        float f[8] = {fmaf(__half2float(xh[0]), a0.x, b0.x), fmaf(__half2float(xh[1]), a0.y, b0.y),
-                      fmaf(__half2float(xh[2]), a0.z, b0.z), fmaf(__half2float(xh[3]), a0.w, b0.w),
-                      fmaf(__half2float(xh[4]), a1.x, b1.x), fmaf(__half2float(xh[5]), a1.y, b1.y),
-                      fmaf(__half2float(xh[6]), a1.z, b1.z), fmaf(__half2float(xh[7]), a1.w, b1.w)};
-        uint4 o;
-        __half2* oh = reinterpret_cast<__half2*>(&o);
+    constexpr int U = 4;                   // independent 16-byte loads in flight per thread
+    for (int i0 = threadIdx.x; i0 < total; i0 += blockDim.x * U) {
+        uint4 v[U];
+        int rr[U], vv[U];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            float u0 = f[2 * e], u1 = f[2 * e + 1];
-            if (silu) {
-                u0 = silu_f(u0);
-                u1 = silu_f(u1);
-            }
-            oh[e] = __floats2half2_rn(u0, u1);
+        for (int u = 0; u < U; ++u) {
+            const int i = i0 + u * blockDim.x;
+            rr[u] = i / C8;
+            vv[u] = i - rr[u] * C8;
+            if (i < total) v[u] = __ldg(reinterpret_cast<const uint4*>(x + (base_row + r0 + rr[u]) * ldx + vv[u] * 8));
         }
-        *reinterpret_cast<uint4*>(y + row * ldy + vc * 8) = o;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int i = i0 + u * blockDim.x;
+            if (i >= total) continue;
+            const int vc = vv[u];
+            const __half* xh = reinterpret_cast<const __half*>(&v[u]);
+            const float4 a0 = *reinterpret_cast<const float4*>(ab + vc * 8);
+            const float4 a1 = *reinterpret_cast<const float4*>(ab + vc * 8 + 4);
+            const float4 b0 = *reinterpret_cast<const float4*>(ab + C + vc * 8);
+            const float4 b1 = *reinterpret_cast<const float4*>(ab + C + vc * 8 + 4);
+            float f[8] = {fmaf(__half2float(xh[0]), a0.x, b0.x), fmaf(__half2float(xh[1]), a0.y, b0.y),
+                          fmaf(__half2float(xh[2]), a0.z, b0.z), fmaf(__half2float(xh[3]), a0.w, b0.w),
+                          fmaf(__half2float(xh[4]), a1.x, b1.x), fmaf(__half2float(xh[5]), a1.y, b1.y),
+                          fmaf(__half2float(xh[6]), a1.z, b1.z), fmaf(__half2float(xh[7]), a1.w, b1.w)};
+            uint4 o;
+            __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                float u0 = f[2 * e], u1 = f[2 * e + 1];
+                if (silu) {
+                    u0 = silu_f(u0);
+                    u1 = silu_f(u1);
+                }
+                oh[e] = __floats2half2_rn(u0, u1);
+            }
+            *reinterpret_cast<uint4*>(y + (base_row + r0 + rr[u]) * ldy + vc * 8) = o;
+        }
     }
 }
 
@@ -250,8 +262,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __half* __restrict
 }  // namespace
 
 int gn_rows_per_chunk(int rows_per_inst, int n_inst, int num_sms) {
-    // aim for >= ~4 blocks per SM, chunks of at least 8 rows
-    long long want = static_cast<long long>(num_sms) * 4;
+    // ~2 blocks per SM: fat blocks amortise the per-block latency chain (few dependent loads per thread otherwise)
+    long long want = static_cast<long long>(num_sms) * 2;
     long long chunks_per_inst = (want + n_inst - 1) / n_inst;
     if (chunks_per_inst < 1) chunks_per_inst = 1;
     long long rpc = (rows_per_inst + chunks_per_inst - 1) / chunks_per_inst;
@@ -285,8 +297,8 @@ int groupnorm_silu(const __half* x, long long ldx, __half* y, long long ldy, lon
         gn_stats_kernel<<<dim3(nchunks, n_inst), kStatsThreads, 2 * C * sizeof(float), stream>>>(
             x, ldx, C, rows_per_inst, rpc, nchunks, eps, partial, counters, stats);
     if (phase == 1) return cudaGetLastError() == cudaSuccess ? 0 : -2;
-    // rows per apply block: ~8 blocks per SM overall, at least 4 rows
-    long long want_blocks = static_cast<long long>(num_sms) * 8;
+    // rows per apply block: ~4 blocks per SM overall, at least 4 rows
+    long long want_blocks = static_cast<long long>(num_sms) * 4;
     long long per_inst = (want_blocks + n_inst - 1) / n_inst;
     if (per_inst < 1) per_inst = 1;
     long long rpb = (rows_per_inst + per_inst - 1) / per_inst;
