@@ -16,20 +16,20 @@ namespace t2v {
 
 namespace {
 
-constexpr int BM = 64;     // queries per CTA (16 per warp)
-constexpr int BNK = 64;    // keys per iteration
 constexpr int HD = 64;     // head dim
-constexpr int kThreads = 128;
+// Tile shapes: TS = 64 (64 queries x 64 keys per iteration, 4 warps) for long sequences; TS = 32 (2 warps) for the short
+// temporal sequences (S = frames = 24 would waste 63 % of a 64 x 64 tile).
 
 // 64 x 64 fp16 tile, 128 B rows, 16 B chunks XOR-swizzled by (row & 7) -> conflict-free ldmatrix
 __device__ __forceinline__ uint32_t tile_off(int row, int chunk) { return row * 128 + ((chunk ^ (row & 7)) << 4); }
 
+template <int TS>
 __device__ __forceinline__ void load_tile(uint32_t smem_tile, const __half* gbase, long long seq_stride, int s0,
                                           int s_len, int tid) {
-    // 64 rows x 8 chunks = 512 x 16 B, 128 threads -> 4 each
+    // TS rows x 8 chunks of 16 B, 2*TS threads -> 4 each
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        const int idx = tid + i * kThreads;
+        const int idx = tid + i * (2 * TS);
         const int row = idx >> 3;
         const int chunk = idx & 7;
         const bool ok = (s0 + row) < s_len;
@@ -38,11 +38,13 @@ __device__ __forceinline__ void load_tile(uint32_t smem_tile, const __half* gbas
     }
 }
 
-__global__ void __launch_bounds__(kThreads) attention_kernel(AttnParams p) {
-    __shared__ __align__(128) uint8_t smem[8192 * 5];   // Q | K0 | K1 | V0 | V1
+template <int TS>
+__global__ void __launch_bounds__(2 * TS) attention_kernel(AttnParams p) {
+    constexpr int BM = TS, BNK = TS, NB = TS / 8, KS = TS / 16, TB = TS * 128;   // tile bytes
+    __shared__ __align__(128) uint8_t smem[TB * 5];   // Q | K0 | K1 | V0 | V1
     const uint32_t sQ = smem_u32(smem);
-    const uint32_t sK[2] = {sQ + 8192, sQ + 16384};
-    const uint32_t sV[2] = {sQ + 24576, sQ + 32768};
+    const uint32_t sK[2] = {sQ + TB, sQ + 2 * TB};
+    const uint32_t sV[2] = {sQ + 3 * TB, sQ + 4 * TB};
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
     const int lane = tid & 31;
@@ -58,9 +60,9 @@ __global__ void __launch_bounds__(kThreads) attention_kernel(AttnParams p) {
     const __half* V = p.v + ko * p.v_bs + ki * p.v_bsi + head * HD;
     __half* O = p.o + bo * p.o_bs + bi * p.o_bsi + head * HD;
 
-    load_tile(sQ, Q, p.q_ss, q0, p.sq, tid);
-    load_tile(sK[0], K, p.k_ss, 0, p.skv, tid);
-    load_tile(sV[0], V, p.v_ss, 0, p.skv, tid);
+    load_tile<TS>(sQ, Q, p.q_ss, q0, p.sq, tid);
+    load_tile<TS>(sK[0], K, p.k_ss, 0, p.skv, tid);
+    load_tile<TS>(sV[0], V, p.v_ss, 0, p.skv, tid);
     cp_async_commit();
 
     const int n_kv = (p.skv + BNK - 1) / BNK;
@@ -78,8 +80,8 @@ __global__ void __launch_bounds__(kThreads) attention_kernel(AttnParams p) {
     for (int it = 0; it < n_kv; ++it) {
         const int cur = it & 1;
         if (it + 1 < n_kv) {
-            load_tile(sK[cur ^ 1], K, p.k_ss, (it + 1) * BNK, p.skv, tid);
-            load_tile(sV[cur ^ 1], V, p.v_ss, (it + 1) * BNK, p.skv, tid);
+            load_tile<TS>(sK[cur ^ 1], K, p.k_ss, (it + 1) * BNK, p.skv, tid);
+            load_tile<TS>(sV[cur ^ 1], V, p.v_ss, (it + 1) * BNK, p.skv, tid);
             cp_async_commit();
             cp_async_wait<1>();
         } else {
@@ -92,15 +94,15 @@ __global__ void __launch_bounds__(kThreads) attention_kernel(AttnParams p) {
                 ldmatrix_x4(qf[ks], sQ + tile_off(warp * 16 + (lane & 15), ks * 2 + (lane >> 4)));
         }
         // ---- S = Q K^T (16 x 64 per warp)
-        float s[8][4];
+        float s[NB][4];
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
+        for (int i = 0; i < NB; ++i)
 #pragma unroll
             for (int j = 0; j < 4; ++j) s[i][j] = 0.f;
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {
 #pragma unroll
-            for (int nb = 0; nb < 8; nb += 2) {
+            for (int nb = 0; nb < NB; nb += 2) {
                 uint32_t kf[4];
                 // lanes 0-7: keys nb*8.., k-chunk 2ks ; 8-15: same keys, chunk 2ks+1 ; 16-31: next 8 keys
                 const int row = nb * 8 + (lane & 7) + ((lane >> 4) << 3);
@@ -116,7 +118,7 @@ __global__ void __launch_bounds__(kThreads) attention_kernel(AttnParams p) {
         const int kbase = it * BNK;
         float m_new[2] = {m_run[0], m_run[1]};
 #pragma unroll
-        for (int nb = 0; nb < 8; ++nb) {
+        for (int nb = 0; nb < NB; ++nb) {
             const int col = kbase + nb * 8 + (lane & 3) * 2;
             if (col >= p.skv) s[nb][0] = s[nb][2] = -INFINITY;
             if (col + 1 >= p.skv) s[nb][1] = s[nb][3] = -INFINITY;
@@ -136,9 +138,9 @@ __global__ void __launch_bounds__(kThreads) attention_kernel(AttnParams p) {
             m_run[r] = m_new[r];
             l_run[r] *= corr[r];
         }
-        uint32_t pf[4][4];          // P as A-fragments for the 4 key k-steps
+        uint32_t pf[KS][4];         // P as A-fragments for the key k-steps (16 keys each)
 #pragma unroll
-        for (int nb = 0; nb < 8; ++nb) {
+        for (int nb = 0; nb < NB; ++nb) {
             const float p0 = exp2f(s[nb][0] * sl2 - msc[0]);
             const float p1 = exp2f(s[nb][1] * sl2 - msc[0]);
             const float p2 = exp2f(s[nb][2] * sl2 - msc[1]);
@@ -159,7 +161,7 @@ __global__ void __launch_bounds__(kThreads) attention_kernel(AttnParams p) {
         }
         // ---- O += P V
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {          // 16 keys per step
+        for (int ks = 0; ks < KS; ++ks) {         // 16 keys per step
 #pragma unroll
             for (int db = 0; db < 8; db += 2) {   // two 8-dim blocks per ldmatrix.x4.trans
                 uint32_t vf[4];
@@ -197,11 +199,13 @@ __global__ void __launch_bounds__(kThreads) attention_kernel(AttnParams p) {
 }  // namespace
 
 int attention(const AttnParams& p, cudaStream_t stream) {
-    if (p.head_dim != HD || p.sq <= 0 || p.skv <= 0 || p.kv_batch_div <= 0) return -1;
-    if (p.b_inner <= 0) return -1;
-    dim3 grid(p.batch, p.heads, (p.sq + BM - 1) / BM);
+    if (p.head_dim != HD || p.sq <= 0 || p.skv <= 0 || p.kv_batch_div <= 0 || p.b_inner <= 0) return -1;
+    const bool small = p.sq <= 32 && p.skv <= 32;
+    const int ts = small ? 32 : 64;
+    dim3 grid(p.batch, p.heads, (p.sq + ts - 1) / ts);
     if (grid.z > 65535 || grid.y > 65535) return -3;
-    attention_kernel<<<grid, kThreads, 0, stream>>>(p);
+    if (small) attention_kernel<32><<<grid, 64, 0, stream>>>(p);
+    else attention_kernel<64><<<grid, 128, 0, stream>>>(p);
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 

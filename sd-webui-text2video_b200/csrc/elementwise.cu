@@ -249,6 +249,42 @@ __global__ void pack_geglu_kernel(const void* w, const void* b, int src_is_f32, 
     }
 }
 
+__global__ void splitk_reduce_kernel(const float* part, int splits, long long split_stride, long long rows, int N8,
+                                     const __half* bias, int bias_rows, long long bias_stride, const __half* residual,
+                                     long long ldr, __half* out, long long ldo) {
+    GRID_STRIDE(i, rows * N8) {
+        const long long r = i / N8;
+        const int c = static_cast<int>(i - r * N8) * 8;
+        float acc[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+        for (int s = 0; s < splits; ++s) {                   // fixed order: deterministic
+            const float4* p = reinterpret_cast<const float4*>(part + s * split_stride + r * (static_cast<long long>(N8) * 8) + c);
+            const float4 a = __ldg(p), b = __ldg(p + 1);
+            acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w;
+            acc[4] += b.x; acc[5] += b.y; acc[6] += b.z; acc[7] += b.w;
+        }
+        if (bias != nullptr) {
+            const __half* bp = bias + (bias_rows > 0 ? (r / bias_rows) * bias_stride : 0) + c;
+            const uint4 bv = __ldg(reinterpret_cast<const uint4*>(bp));
+            const __half* bh = reinterpret_cast<const __half*>(&bv);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[e] += __half2float(bh[e]);
+        }
+        if (residual != nullptr) {
+            const uint4 rv = __ldg(reinterpret_cast<const uint4*>(residual + r * ldr + c));
+            const __half* rh = reinterpret_cast<const __half*>(&rv);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[e] += __half2float(rh[e]);
+        }
+        uint4 o;
+        __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) oh[e] = __floats2half2_rn(acc[2 * e], acc[2 * e + 1]);
+        *reinterpret_cast<uint4*>(out + r * ldo + c) = o;
+    }
+}
+
 __global__ void convert_kernel(const void* src, int src_is_f32, __half* dst, long long n) {
     GRID_STRIDE(i, n) {
         dst[i] = src_is_f32 ? __float2half_rn(reinterpret_cast<const float*>(src)[i]) : reinterpret_cast<const __half*>(src)[i];
@@ -387,6 +423,14 @@ int pack_geglu_weight(const void* w, const void* b, int src_is_f32, __half* wdst
                       cudaStream_t stream) {
     if ((2 * H) % bn) return -1;
     pack_geglu_kernel<<<grid_for(static_cast<long long>(2) * H * K, 256), 256, 0, stream>>>(w, b, src_is_f32, wdst, bdst, H, K, bn);
+    return ok();
+}
+int splitk_reduce(const float* part, int splits, long long split_stride, long long rows, int N, const __half* bias,
+                  int bias_rows, long long bias_stride, const __half* residual, long long ldr, __half* out, long long ldo,
+                  cudaStream_t stream) {
+    if ((N & 7) || (ldo & 7) || (residual && (ldr & 7)) || (bias && (bias_stride & 7))) return -1;
+    splitk_reduce_kernel<<<grid_for(rows * (N / 8), 256), 256, 0, stream>>>(part, splits, split_stride, rows, N / 8, bias,
+                                                                            bias_rows, bias_stride, residual, ldr, out, ldo);
     return ok();
 }
 int convert_to_f16(const void* src, int src_is_f32, __half* dst, long long n, cudaStream_t stream) {

@@ -77,17 +77,22 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
 
     // work items: (pair of consecutive M-tiles, N-tile); CTA `rank` of the pair owns M-tile 2*pm + rank
     const int pairs_m = (g.tiles_m + CG - 1) / CG;
-    const int total_pairs = pairs_m * g.tiles_n;
+    const int nsplit = g.splits > 1 ? g.splits : 1;
+    const int total_pairs = pairs_m * g.tiles_n * nsplit;      // work items: (pair of M-tiles, N-tile, K split)
     const int first_pair = blockIdx.x / CG;
     const int pair_stride = gridDim.x / CG;
-    const int k_iters = g.ntaps * g.k_chunks;
+    const int k_total = g.ntaps * g.k_chunks;
+    const int k_per = g.splits > 1 ? g.k_per_split : k_total;
 
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int pt = first_pair; pt < total_pairs; pt += pair_stride) {
+            for (int wi = first_pair; wi < total_pairs; wi += pair_stride) {
+                const int sp = wi % nsplit;
+                const int pt = wi / nsplit;
+                const int it0 = sp * k_per, it1 = min(k_total, it0 + k_per);
                 const int tn = pt % g.tiles_n;
                 const int tmi = (pt / g.tiles_n) * CG + static_cast<int>(rank);
                 int tm = tmi;
@@ -100,12 +105,14 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
                 }
                 if (tmi >= g.tiles_m) org[0] = g.dim[0];       // odd tail: this CTA's half is all out of bounds (zeros)
                 const int bbatch = g.b_batch_dim >= 0 ? org[g.b_batch_dim] : 0;
-                for (int tap = 0; tap < g.ntaps; ++tap) {
-                    const int c1 = org[0] + g.tap_off[tap][0];
-                    const int c2 = org[1] + g.tap_off[tap][1];
-                    const int c3 = org[2] + g.tap_off[tap][2];
-                    const int c4 = org[3] + g.tap_off[tap][3];
-                    for (int kc = 0; kc < g.k_chunks; ++kc) {
+                {
+                    for (int it = it0; it < it1; ++it) {
+                        const int tap = it / g.k_chunks;
+                        const int kc = it - tap * g.k_chunks;
+                        const int c1 = org[0] + g.tap_off[tap][0];
+                        const int c2 = org[1] + g.tap_off[tap][1];
+                        const int c3 = org[2] + g.tap_off[tap][2];
+                        const int c4 = org[3] + g.tap_off[tap][3];
                         mbar_wait(&empty[stage], phase ^ 1u);
                         uint8_t* sa = smem + stage * C::kStageBytes;
                         uint8_t* sb = sa + kABytes;
@@ -147,7 +154,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         uint32_t phase = 0;
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int pt = first_pair; pt < total_pairs; pt += pair_stride) {
+        for (int wi = first_pair; wi < total_pairs; wi += pair_stride) {
+            const int it0s = (wi % nsplit) * k_per;
+            const int k_iters = min(k_total, it0s + k_per) - it0s;
             mbar_wait(&tempty[acc], acc_phase ^ 1u);      // epilogue(s) have drained this accumulator stage
             tc_fence_after();
             const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * 256);
@@ -215,7 +224,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         // accumulator); per-sample bias rows (time-embedding add of the ResBlock convs) are read per thread.
         const bool bias_staged = (g.bias != nullptr) && (g.bias_rows == 0);
         const int et = static_cast<int>(threadIdx.x) - 64;       // 0..255 among the epilogue threads
-        for (int pt = first_pair; pt < total_pairs; pt += pair_stride) {
+        for (int wi = first_pair; wi < total_pairs; wi += pair_stride) {
+            const int sp = wi % nsplit;
+            const int pt = wi / nsplit;
             const int tn = pt % g.tiles_n;
             const int tmi = (pt / g.tiles_n) * CG + static_cast<int>(rank);
             int tm = tmi;
@@ -353,10 +364,23 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
                         }
                     }
                     if (out_f32) {
-                        float* op = reinterpret_cast<float*>(g.out) + grow * g.ldo + ocol;
+                        float* op = reinterpret_cast<float*>(g.out) + sp * g.split_stride + grow * g.ldo + ocol;
+                        if (((g.ldo & 7) == 0) && ((nvalid & 7) == 0) && ((g.split_stride & 7) == 0) &&
+                            ((reinterpret_cast<uintptr_t>(g.out) & 31) == 0)) {
 #pragma unroll
-                        for (int j = 0; j < CW; ++j)
-                            if (ocol + j < nvalid) op[j] = v[j];
+                            for (int j = 0; j < CW; j += 8) {
+                                if (ocol + j < nvalid) {
+                                    U32x8 ov;
+#pragma unroll
+                                    for (int e = 0; e < 8; ++e) ov.v[e] = __float_as_uint(v[j + e]);
+                                    stg_256(op + j, ov);
+                                }
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < CW; ++j)
+                                if (ocol + j < nvalid) op[j] = v[j];
+                        }
                     } else {
                         __half* op = reinterpret_cast<__half*>(g.out) + grow * g.ldo + ocol;
                         if (vec32) {
@@ -545,6 +569,8 @@ int gemm_plan(const GemmProblem& p, GemmPlan* plan, int num_sms) {
     g.residual = p.residual;
     g.ldr = p.ldr;
     g.alpha = p.alpha == 0.f ? 1.0f : p.alpha;
+    g.splits = p.splits > 1 ? p.splits : 1;
+    g.split_stride = p.split_stride;
 
     // ---- N tiling: widest tile that keeps the machine full
     int bn = p.force_bn;
@@ -609,7 +635,10 @@ int gemm_plan(const GemmProblem& p, GemmPlan* plan, int num_sms) {
     }
     const Variant* var = find_variant(bn, (p.flags & GEMM_GEGLU) != 0, plan->cg);
     if (var == nullptr) return -7;
-    const long long pairs = static_cast<long long>((g.tiles_m + plan->cg - 1) / plan->cg) * g.tiles_n;
+    const int kt = g.ntaps * g.k_chunks;
+    g.k_per_split = (kt + g.splits - 1) / g.splits;
+    g.splits = (kt + g.k_per_split - 1) / g.k_per_split;      // no empty splits
+    const long long pairs = static_cast<long long>((g.tiles_m + plan->cg - 1) / plan->cg) * g.tiles_n * g.splits;
     plan->grid = plan->cg * static_cast<int>(std::min<long long>(pairs, num_sms / plan->cg));
     plan->smem = var->smem;
     plan->flops = 2.0 * static_cast<double>(rows) * p.N * p.K * p.ntaps;

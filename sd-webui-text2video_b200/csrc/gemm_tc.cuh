@@ -51,6 +51,9 @@ struct GemmDesc {
     const __half* residual;          // [rows, ldr] or null
     long long ldr;
     float alpha;                     // accumulator scale applied before bias (1.0 normally)
+    int splits;                      // split-K: work item = (tile, split); each split owns k_per_split k-iterations and
+    int k_per_split;                 //   stores its fp32 partial tile at out + split * split_stride (reduced by splitk_reduce)
+    long long split_stride;
 };
 
 struct GemmProblem {
@@ -77,6 +80,8 @@ struct GemmProblem {
     float alpha;
     int force_bn;                    // 0 = auto
     int force_cg;                    // 0 = auto, 1 / 2
+    int splits;                      // 0/1 = no split-K; >1: out must be fp32 [splits][rows][ldo], no bias/residual/GEGLU
+    long long split_stride;          // elements between split partials
 };
 
 struct GemmPlan {

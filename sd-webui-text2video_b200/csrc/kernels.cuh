@@ -67,6 +67,11 @@ int pack_geglu_weight(const void* w, const void* b, int src_is_f32, __half* wdst
                       cudaStream_t stream);
 int convert_to_f16(const void* src, int src_is_f32, __half* dst, long long n, cudaStream_t stream);
 
+// out[r, n] = fp16( sum_s part[s][r][n] + bias[(r / bias_rows) * bias_stride + n] + residual[r, n] )  (split-K fix-up)
+int splitk_reduce(const float* part, int splits, long long split_stride, long long rows, int N, const __half* bias,
+                  int bias_rows, long long bias_stride, const __half* residual, long long ldr, __half* out, long long ldo,
+                  cudaStream_t stream);
+
 // sampler updates (fp32 latents [B,C,F,h,w]; eps from the UNet in fp16, cond / uncond)
 struct DdimStepParams {
     const float* x;           // x_t

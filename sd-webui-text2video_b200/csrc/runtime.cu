@@ -198,6 +198,41 @@ void* Builder::alloc_bytes(size_t bytes) { return arena_->alloc(bytes); }
 int Builder::gemm(GemmProblem& p) {
     double rows = 1;
     for (int d = 0; d < p.nd; ++d) rows *= p.dim[d];
+    // Split-K for contractions whose output cannot fill the machine (low-resolution levels: rows = 768 / 3072 with K up to
+    // 23040): each (tile, split) work item accumulates a K range into an fp32 partial, a fix-up kernel folds the partials
+    // in a fixed order and applies bias / residual.  Deterministic; chosen only when >= half of the SMs would idle.
+    static const bool no_split = getenv("T2V_NO_SPLITK") != nullptr;
+    if (!no_split && p.splits <= 1 && !(p.flags & (GEMM_GEGLU | GEMM_OUT_F32)) && p.b_batch_dim < 0 && (p.N % 8) == 0 &&
+        p.alpha == 1.0f) {
+        const long long tiles_m = (static_cast<long long>(rows) + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M;
+        const long long tiles = tiles_m * ((p.N + 255) / 256);
+        const int kt = p.ntaps * ((p.K + GEMM_BLOCK_K - 1) / GEMM_BLOCK_K);
+        int S = static_cast<int>(std::min<long long>(std::min<long long>(sms_ / std::max<long long>(tiles, 1), kt / 4), 8));
+        if (tiles * 2 <= sms_ && S >= 2) {
+            const long long nrows = static_cast<long long>(rows);
+            float* scratch = reinterpret_cast<float*>(arena_->alloc(static_cast<size_t>(S) * nrows * p.N * sizeof(float)));
+            GemmProblem q = p;
+            q.out = scratch;
+            q.ldo = p.N;
+            q.flags |= GEMM_OUT_F32;
+            q.bias = nullptr;
+            q.bias_rows = 0;
+            q.residual = nullptr;
+            q.splits = S;
+            q.split_stride = nrows * p.N;
+            q.force_bn = 256;
+            const int rc = gemm(q);
+            if (rc != 0) return rc;
+            const GemmProblem o = p;
+            const int N = p.N;
+            step([=](cudaStream_t s) {
+                return splitk_reduce(scratch, S, nrows * N, nrows, N, o.bias, o.bias_rows, o.bias_stride, o.residual, o.ldr,
+                                     reinterpret_cast<__half*>(o.out), o.ldo, s);
+            }, 1, STEP_OTHER, 0.0, "splitk_reduce");
+            arena_->free(reinterpret_cast<char*>(scratch));
+            return 0;
+        }
+    }
     plan_->flops += 2.0 * rows * p.N * p.K * p.ntaps;
     if (dry_) {
         plan_->launches += 1;
@@ -211,8 +246,9 @@ int Builder::gemm(GemmProblem& p) {
         return rc;
     }
     char lab[192];
-    snprintf(lab, sizeof(lab), "gemm rows=%.0f N=%d K=%d taps=%d bn=%d tiles=%dx%d grid=%d%s%s", rows, p.N, p.K, p.ntaps, gp.bn,
-             gp.desc.tiles_m, gp.desc.tiles_n, gp.grid, (p.flags & GEMM_GEGLU) ? " geglu" : "", p.residual ? " +res" : "");
+    snprintf(lab, sizeof(lab), "gemm rows=%.0f N=%d K=%d taps=%d bn=%d tiles=%dx%d grid=%d%s%s%s", rows, p.N, p.K, p.ntaps, gp.bn,
+             gp.desc.tiles_m, gp.desc.tiles_n, gp.grid, (p.flags & GEMM_GEGLU) ? " geglu" : "", p.residual ? " +res" : "",
+             gp.desc.splits > 1 ? " splitK" : "");
     plan_->steps.push_back(StepRec{[gp](cudaStream_t s) { return gemm_launch(gp, s); }, STEP_GEMM, gp.flops, lab});
     plan_->launches += 1;
     return 0;
