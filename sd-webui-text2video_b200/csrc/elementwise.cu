@@ -285,6 +285,31 @@ __global__ void splitk_reduce_kernel(const float* part, int splits, long long sp
     }
 }
 
+// one warp per output row n
+__global__ void __launch_bounds__(256) fold_ln_kernel(const __half* w, const __half* bias, const __half* gamma, const __half* beta,
+                                                      __half* wout, float* colsum, float* bias32, int N, int K) {
+    const int lane = threadIdx.x & 31;
+    const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (n >= N) return;
+    float cs = 0.f, bs = 0.f;
+    for (int k = lane; k < K; k += 32) {
+        const float wv = __half2float(w[static_cast<long long>(n) * K + k]);
+        const __half ws = __float2half_rn(wv * __half2float(gamma[k]));
+        wout[static_cast<long long>(n) * K + k] = ws;
+        cs += __half2float(ws);                 // column sum of EXACTLY what the tensor cores will multiply by
+        bs += wv * __half2float(beta[k]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        cs += __shfl_xor_sync(0xffffffffu, cs, o);
+        bs += __shfl_xor_sync(0xffffffffu, bs, o);
+    }
+    if (lane == 0) {
+        colsum[n] = cs;
+        bias32[n] = bs + (bias != nullptr ? __half2float(bias[n]) : 0.f);
+    }
+}
+
 __global__ void convert_kernel(const void* src, int src_is_f32, __half* dst, long long n) {
     GRID_STRIDE(i, n) {
         dst[i] = src_is_f32 ? __float2half_rn(reinterpret_cast<const float*>(src)[i]) : reinterpret_cast<const __half*>(src)[i];
@@ -431,6 +456,11 @@ int splitk_reduce(const float* part, int splits, long long split_stride, long lo
     if ((N & 7) || (ldo & 7) || (residual && (ldr & 7)) || (bias && (bias_stride & 7))) return -1;
     splitk_reduce_kernel<<<grid_for(rows * (N / 8), 256), 256, 0, stream>>>(part, splits, split_stride, rows, N / 8, bias,
                                                                             bias_rows, bias_stride, residual, ldr, out, ldo);
+    return ok();
+}
+int fold_ln_into_linear(const __half* w, const __half* bias, const __half* gamma, const __half* beta, __half* wout,
+                        float* colsum, float* bias32, int N, int K, cudaStream_t stream) {
+    fold_ln_kernel<<<(N + 7) / 8, 256, 0, stream>>>(w, bias, gamma, beta, wout, colsum, bias32, N, K);
     return ok();
 }
 int convert_to_f16(const void* src, int src_is_f32, __half* dst, long long n, cudaStream_t stream) {

@@ -28,7 +28,7 @@ struct Cfg {
     static constexpr int kBBytes = (BN / CG) * GEMM_BLOCK_K * 2;      // a CTA of a pair stages half of the B tile
     static constexpr int kStageBytes = kABytes + kBBytes;
     static constexpr int kStages = (kSmemBudget / kStageBytes) > 8 ? 8 : (kSmemBudget / kStageBytes);
-    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + 2048 /*bias tiles*/;
+    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + 4096 /*bias + colsum tiles*/;
 };
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
@@ -48,6 +48,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     uint64_t* tempty = tfull + 2;                // [2] epilogue -> MMA
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
     float* bias_s = reinterpret_cast<float*>(bars) + 64;         // [2 accumulator stages][256] fp32 bias tile (256 B after the barriers)
+    float* csum_s = bias_s + 512;                                // [2][256] column sums of the gamma-scaled weights (GEMM_LN)
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -222,7 +223,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
                            (g.residual == nullptr || (((g.ldr & 15) == 0) && ((reinterpret_cast<uintptr_t>(g.residual) & 31) == 0)));
         // A bias shared by all rows is staged once per tile in smem (its L2 latency hides behind the wait for the
         // accumulator); per-sample bias rows (time-embedding add of the ResBlock convs) are read per thread.
-        const bool bias_staged = (g.bias != nullptr) && (g.bias_rows == 0);
+        const bool ln = (g.flags & GEMM_LN) != 0;
+        const bool bias_staged = ln || ((g.bias != nullptr) && (g.bias_rows == 0));
         const int et = static_cast<int>(threadIdx.x) - 64;       // 0..255 among the epilogue threads
         for (int wi = first_pair; wi < total_pairs; wi += pair_stride) {
             const int sp = wi % nsplit;
@@ -278,17 +280,30 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
                 }
             };
             if (hsel < nchunks) prefetch_res(hsel);
-            float bstage = 0.f;
+            float bstage = 0.f, cstage = 0.f;
             if (bias_staged && et < BN) {
                 const int col = tn * BN + et;
-                if (col < g.N) bstage = __half2float(__ldg(g.bias + col));
+                if (col < g.N) {
+                    if (ln) {
+                        bstage = __ldg(g.bias32 + col);
+                        cstage = __ldg(g.colsum + col);
+                    } else {
+                        bstage = __half2float(__ldg(g.bias + col));
+                    }
+                }
             }
+            float2 rs = make_float2(0.f, 1.f);                    // (mean, rstd) of this thread's row
+            if (ln && valid) rs = __ldg(g.rowstat + grow);
 
             mbar_wait(&tfull[acc], acc_phase);
             tc_fence_after();
             const float* bs = bias_s + acc * 256;
+            const float* cs = csum_s + acc * 256;
             if (bias_staged) {
-                if (et < BN) bias_s[acc * 256 + et] = bstage;
+                if (et < BN) {
+                    bias_s[acc * 256 + et] = bstage;
+                    if (ln) csum_s[acc * 256 + et] = cstage;
+                }
                 asm volatile("bar.sync 1, 256;" ::: "memory");     // epilogue warps only (named barrier 1)
             }
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * 256);
@@ -328,12 +343,18 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
                 }
                 tmem_ld_wait();
                 float v[CW];
+                if (ln) {
 #pragma unroll
-                for (int j = 0; j < CW; ++j) v[j] = fmaf(__uint_as_float(u[j]), g.alpha, bv[j]);
+                    for (int j = 0; j < CW; ++j) v[j] = fmaf(rs.y, fmaf(-rs.x, cs[c0 + j], __uint_as_float(u[j])), bv[j]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < CW; ++j) v[j] = fmaf(__uint_as_float(u[j]), g.alpha, bv[j]);
+                }
                 if (geglu) {
 #pragma unroll
                     for (int j = 0; j < CW; ++j) {
-                        const float gt = fmaf(__uint_as_float(ug[j]), g.alpha, bg[j]);
+                        const float gt = ln ? fmaf(rs.y, fmaf(-rs.x, cs[BN / 2 + c0 + j], __uint_as_float(ug[j])), bg[j])
+                                            : fmaf(__uint_as_float(ug[j]), g.alpha, bg[j]);
                         // reference rounding points (fp16 autocast): proj output, gelu output, product
                         const float xa = __half2float(__float2half_rn(v[j]));
                         const float ga = __half2float(__float2half_rn(gt));
@@ -569,6 +590,9 @@ int gemm_plan(const GemmProblem& p, GemmPlan* plan, int num_sms) {
     g.residual = p.residual;
     g.ldr = p.ldr;
     g.alpha = p.alpha == 0.f ? 1.0f : p.alpha;
+    g.rowstat = p.rowstat;
+    g.colsum = p.colsum;
+    g.bias32 = p.bias32;
     g.splits = p.splits > 1 ? p.splits : 1;
     g.split_stride = p.split_stride;
 

@@ -23,6 +23,8 @@ constexpr int GEMM_MAX_RDIMS = 4;
 enum GemmFlags : int {
     GEMM_GEGLU = 1,        // epilogue: out[:, j] = (acc[:, j] + b) * gelu(acc[:, BN/2 + j] + b)  (weights interleaved per tile)
     GEMM_OUT_F32 = 2,      // store fp32 instead of fp16
+    GEMM_LN = 4,           // LayerNorm of the A rows folded into the epilogue: out = rstd_r * (acc - mean_r * colsum_n) + bias32_n
+                           //   (weights pre-scaled by gamma; colsum_n = sum_k W'[n,k]; bias32_n = sum_k W[n,k] beta_k + bias_n)
     // bring-up / performance-isolation switches (never set by the model code)
     GEMM_DBG_NO_STORE = 256,   // epilogue skips the global stores
     GEMM_DBG_NO_EPI = 512,     // epilogue releases the accumulator without reading it
@@ -51,6 +53,9 @@ struct GemmDesc {
     const __half* residual;          // [rows, ldr] or null
     long long ldr;
     float alpha;                     // accumulator scale applied before bias (1.0 normally)
+    const float2* rowstat;           // GEMM_LN: (mean, rstd) per global row
+    const float* colsum;             // GEMM_LN: per packed column
+    const float* bias32;             // GEMM_LN: per packed column (replaces `bias`)
     int splits;                      // split-K: work item = (tile, split); each split owns k_per_split k-iterations and
     int k_per_split;                 //   stores its fp32 partial tile at out + split * split_stride (reduced by splitk_reduce)
     long long split_stride;
@@ -80,6 +85,9 @@ struct GemmProblem {
     float alpha;
     int force_bn;                    // 0 = auto
     int force_cg;                    // 0 = auto, 1 / 2
+    const float2* rowstat;           // GEMM_LN operands (see GemmFlags)
+    const float* colsum;
+    const float* bias32;
     int splits;                      // 0/1 = no split-K; >1: out must be fp32 [splits][rows][ldo], no bias/residual/GEGLU
     long long split_stride;          // elements between split partials
 };

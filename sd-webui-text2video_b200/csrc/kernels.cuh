@@ -15,6 +15,9 @@ int groupnorm_silu(const __half* x, long long ldx, __half* y, long long ldy, lon
 int layernorm(const __half* x, long long ldx, __half* y, long long ldy, long long rows, int C, const __half* gamma,
               const __half* beta, float eps, cudaStream_t stream);
 
+// (mean, rstd) of every row of x over C (LayerNorm statistics; the normalisation itself is folded into the consuming GEMM)
+int layernorm_rowstats(const __half* x, long long ldx, long long rows, int C, float eps, float2* out, cudaStream_t stream);
+
 // ---------------------------------------------------------------- attention.cu
 struct AttnParams {
     const __half* q;
@@ -66,6 +69,10 @@ int pack_conv_weight(const void* src, int src_is_f32, __half* dst, int Cout, int
 int pack_geglu_weight(const void* w, const void* b, int src_is_f32, __half* wdst, __half* bdst, int H, int K, int bn,
                       cudaStream_t stream);
 int convert_to_f16(const void* src, int src_is_f32, __half* dst, long long n, cudaStream_t stream);
+// LayerNorm folded into a Linear: wout[n,k] = fp16(w[n,k] * gamma[k]); colsum[n] = sum_k wout[n,k];
+// bias32[n] = sum_k w[n,k] * beta[k] (+ bias[n])
+int fold_ln_into_linear(const __half* w, const __half* bias, const __half* gamma, const __half* beta, __half* wout,
+                        float* colsum, float* bias32, int N, int K, cudaStream_t stream);
 
 // out[r, n] = fp16( sum_s part[s][r][n] + bias[(r / bias_rows) * bias_stride + n] + residual[r, n] )  (split-K fix-up)
 int splitk_reduce(const float* part, int splits, long long split_stride, long long rows, int N, const __half* bias,

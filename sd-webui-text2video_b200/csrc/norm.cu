@@ -259,6 +259,49 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __half* __restrict
     }
 }
 
+__global__ void __launch_bounds__(256) ln_rowstats_kernel(const __half* __restrict__ x, long long ldx, long long rows, int C,
+                                                          float eps, float2* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const long long row = blockIdx.x * static_cast<long long>(blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int C8 = C >> 3;
+    constexpr int MAXV = 8;
+    uint4 v[MAXV];
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < MAXV; ++k) {
+        const int vc = lane + k * 32;
+        if (vc < C8) {
+            v[k] = __ldg(reinterpret_cast<const uint4*>(x + row * ldx + vc * 8));
+            const __half2* h2 = reinterpret_cast<const __half2*>(&v[k]);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float2 f = __half22float2(h2[e]);
+                s += f.x + f.y;
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s / C;
+    float q = 0.f;
+#pragma unroll
+    for (int k = 0; k < MAXV; ++k) {
+        const int vc = lane + k * 32;
+        if (vc < C8) {
+            const __half2* h2 = reinterpret_cast<const __half2*>(&v[k]);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float2 f = __half22float2(h2[e]);
+                q += (f.x - mean) * (f.x - mean) + (f.y - mean) * (f.y - mean);
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    if (lane == 0) out[row] = make_float2(mean, rsqrtf(q / C + eps));
+}
+
 }  // namespace
 
 int gn_rows_per_chunk(int rows_per_inst, int n_inst, int num_sms) {
@@ -306,6 +349,12 @@ int groupnorm_silu(const __half* x, long long ldx, __half* y, long long ldy, lon
     const int nblk = static_cast<int>((rows_per_inst + rpb - 1) / rpb);
     gn_apply_kernel<<<dim3(nblk, n_inst), 256, 2 * C * sizeof(float), stream>>>(x, ldx, y, ldy, C, rows_per_inst,
                                                                               static_cast<int>(rpb), stats, gamma, beta, silu);
+    return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
+int layernorm_rowstats(const __half* x, long long ldx, long long rows, int C, float eps, float2* out, cudaStream_t stream) {
+    if (C % 8 != 0 || C > 2048) return -1;
+    ln_rowstats_kernel<<<static_cast<unsigned int>((rows + 7) / 8), 256, 0, stream>>>(x, ldx, rows, C, eps, out);
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 

@@ -202,7 +202,7 @@ int Builder::gemm(GemmProblem& p) {
     // 23040): each (tile, split) work item accumulates a K range into an fp32 partial, a fix-up kernel folds the partials
     // in a fixed order and applies bias / residual.  Deterministic; chosen only when >= half of the SMs would idle.
     static const bool no_split = getenv("T2V_NO_SPLITK") != nullptr;
-    if (!no_split && p.splits <= 1 && !(p.flags & (GEMM_GEGLU | GEMM_OUT_F32)) && p.b_batch_dim < 0 && (p.N % 8) == 0 &&
+    if (!no_split && p.splits <= 1 && !(p.flags & (GEMM_GEGLU | GEMM_OUT_F32 | GEMM_LN)) && p.b_batch_dim < 0 && (p.N % 8) == 0 &&
         p.alpha == 1.0f) {
         const long long tiles_m = (static_cast<long long>(rows) + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M;
         const long long tiles = tiles_m * ((p.N + 255) / 256);
@@ -525,6 +525,54 @@ Tok layer_norm(NetCtx& c, const Tok& x, const std::string& prefix) {
     return y;
 }
 
+
+Tok ln_linear(NetCtx& c, const Tok& x, const std::string& ln_prefix, const std::string& key, const __half* w_src,
+              const __half* bias_src, int N, const Tok* residual, int flags, int force_bn) {
+    ParamStore& P = *c.params;
+    const int K = x.C;
+    const __half* wf = nullptr;
+    const float* cs = nullptr;
+    const float* b32 = nullptr;
+    if (!c.b->dry()) {
+        const std::string k = key + "#lnfold:" + ln_prefix;
+        __half* w = P.packed(k);
+        if (w == nullptr) {
+            w = P.new_packed(k, static_cast<long long>(N) * K);
+            __half* csh = P.new_packed(k + "#cs", 2LL * N);        // fp32 arrays live in the same cache (2 halves each)
+            __half* bsh = P.new_packed(k + "#b32", 2LL * N);
+            if (!w || !csh || !bsh ||
+                fold_ln_into_linear(w_src, bias_src, prm(c, ln_prefix + ".weight"), prm(c, ln_prefix + ".bias"), w,
+                                    reinterpret_cast<float*>(csh), reinterpret_cast<float*>(bsh), N, K, c.stream) != 0)
+                c.b->error = -12;
+        }
+        wf = w;
+        cs = reinterpret_cast<const float*>(P.packed(k + "#cs"));
+        b32 = reinterpret_cast<const float*>(P.packed(k + "#b32"));
+    }
+    float2* stats = reinterpret_cast<float2*>(c.b->alloc_bytes(static_cast<size_t>(x.rows) * sizeof(float2)));
+    {
+        const Tok xx = x;
+        char lab[96];
+        snprintf(lab, sizeof(lab), "ln_rowstats rows=%lld C=%d", x.rows, x.C);
+        c.b->step([=](cudaStream_t s) { return layernorm_rowstats(xx.p, xx.ld, xx.rows, xx.C, 1e-5f, stats, s); }, 1, STEP_NORM,
+                  0.0, lab);
+    }
+    const int ncols = (flags & GEMM_GEGLU) ? N / 2 : N;
+    Tok y = c.b->alloc(x.rows, ncols);
+    GemmProblem p = base_problem(x, K, wf, N, N, y);
+    p.flags = flags | GEMM_LN;
+    p.rowstat = stats;
+    p.colsum = cs;
+    p.bias32 = b32;
+    p.force_bn = force_bn;
+    if (residual) {
+        p.residual = residual->p;
+        p.ldr = residual->ld;
+    }
+    c.b->gemm(p);
+    c.b->free_bytes(stats);
+    return y;
+}
 
 Tok conv3x3(NetCtx& c, const Tok& x, const std::string& wname, const __half* bias, int bias_rows, long long bias_stride,
             int N, int hcur, int wcur, const Tok* residual, int n_alloc) {

@@ -137,6 +137,11 @@ GemmProblem base_problem(const Tok& a, int K, const __half* w, int n_alloc, int 
 Tok linear(NetCtx& c, const Tok& x, const __half* w, int N, const __half* bias, const Tok* residual, int K = 0);
 Tok group_norm(NetCtx& c, const Tok& x, const std::string& prefix, long long rows_per_inst, float eps, bool silu);
 Tok layer_norm(NetCtx& c, const Tok& x, const std::string& prefix);
+// y = Linear(LayerNorm(x)) (+residual) with the normalisation folded into the GEMM: a row-statistics kernel (reads x once)
+// + one GEMM on the RAW rows whose epilogue applies rstd * (acc - mean * colsum) + bias'.  `w_src` [N, K] / `bias_src` are
+// the (already concatenated / GEGLU-interleaved) weights; the gamma/beta-folded copy is cached under `key`.
+Tok ln_linear(NetCtx& c, const Tok& x, const std::string& ln_prefix, const std::string& key, const __half* w_src,
+              const __half* bias_src, int N, const Tok* residual, int flags = 0, int force_bn = 0);
 Tok conv3x3(NetCtx& c, const Tok& x, const std::string& wname, const __half* bias, int bias_rows, long long bias_stride,
             int N, int hcur, int wcur, const Tok* residual, int n_alloc = 0);
 

@@ -237,7 +237,7 @@ Tok transformer_block(Ctx& c, Tok x, const std::string& p, int heads, int hcur, 
     const float scale = 0.125f;    // head_dim^-0.5, head_dim = 64 (t2v_model.py:530)
     for (int a = 0; a < 2; ++a) {
         const std::string ap = p + (a == 0 ? ".attn1" : ".attn2");
-        Tok l = layer_norm(c, x, p + (a == 0 ? ".norm1" : ".norm2"));
+        const std::string lnp = p + (a == 0 ? ".norm1" : ".norm2");
         const bool self_attn = (a == 0) || temporal;
         Tok o = c.b->alloc(R, C);
         AttnParams ap_;
@@ -250,7 +250,7 @@ Tok transformer_block(Ctx& c, Tok x, const std::string& p, int heads, int hcur, 
         Tok qkv, kv;
         if (self_attn) {
             const __half* wqkv = w_cat(c, {ap + ".to_q.weight", ap + ".to_k.weight", ap + ".to_v.weight"});
-            qkv = linear(c, l, wqkv, 3 * C, nullptr, nullptr);
+            qkv = ln_linear(c, x, lnp, ap + ".qkv", wqkv, nullptr, 3 * C, nullptr);
             ap_.q = qkv.p;
             ap_.k = qkv.p + C;
             ap_.v = qkv.p + 2 * C;
@@ -276,7 +276,7 @@ Tok transformer_block(Ctx& c, Tok x, const std::string& p, int heads, int hcur, 
         } else {
             const Param& wk = c.params->get(ap + ".to_k.weight");
             const int ctx_dim = wk.data ? static_cast<int>(wk.shape[1]) : c.u->cfg.context_dim;
-            qkv = linear(c, l, prm(c, ap + ".to_q.weight"), C, nullptr, nullptr);
+            qkv = ln_linear(c, x, lnp, ap + ".to_q", prm(c, ap + ".to_q.weight"), nullptr, C, nullptr);
             // K/V of the prompt: identical for every frame (the reference recomputes them per frame, :426,:545-546)
             Tok ctx_tok;
             ctx_tok.p = c.ctx;
@@ -300,7 +300,6 @@ Tok transformer_block(Ctx& c, Tok x, const std::string& p, int heads, int hcur, 
             ap_.o_bs = P * o.ld;
             ap_.o_ss = o.ld;
         }
-        c.b->free(l);
         {
             const AttnParams apc = ap_;
             c.b->step([apc](cudaStream_t s) { return attention(apc, s); }, 1, STEP_ATTN,
@@ -315,19 +314,10 @@ Tok transformer_block(Ctx& c, Tok x, const std::string& p, int heads, int hcur, 
         x = y;
     }
     // feed-forward: GEGLU fused into the first GEMM's epilogue (t2v_model.py:813-821, :833-846)
-    Tok l = layer_norm(c, x, p + ".norm3");
     const int H = 4 * C;
     const int bn = (2 * H) % 256 == 0 ? 256 : ((2 * H) % 128 == 0 ? 128 : 64);
     Geglu g = w_geglu(c, p + ".ff.net.0.proj", H, C, bn);
-    Tok gg = c.b->alloc(R, H);
-    {
-        GemmProblem pr = base_problem(l, C, g.w, 2 * H, 2 * H, gg);
-        pr.bias = g.b;
-        pr.flags = GEMM_GEGLU;
-        pr.force_bn = bn;
-        c.b->gemm(pr);
-    }
-    c.b->free(l);
+    Tok gg = ln_linear(c, x, p + ".norm3", p + ".ff.net.0.proj#geglu" + std::to_string(bn), g.w, g.b, 2 * H, nullptr, GEMM_GEGLU, bn);
     Tok y = linear(c, gg, prm(c, p + ".ff.net.2.weight"), C, prm(c, p + ".ff.net.2.bias"), &x);
     c.b->free(gg);
     c.b->free(x);
