@@ -19,7 +19,10 @@ namespace t2v {
 
 namespace {
 
-constexpr int kThreads = 320;   // TMA warp + MMA warp + 8 epilogue warps
+// TMA warp + MMA warp + EW epilogue warps.  EW = 8 normally; the GEGLU epilogue (erf, three fp16 rounding points per
+// element) is issue/latency bound at small K, so it runs 16 warps on 16-column chunks (register budget 65536/576 = 113).
+constexpr int epi_warps(bool geglu) { return geglu ? 16 : 8; }
+constexpr int n_threads(bool geglu) { return 64 + 32 * epi_warps(geglu); }
 constexpr int kABytes = GEMM_BLOCK_M * GEMM_BLOCK_K * 2;   // 16 KB
 constexpr int kSmemBudget = 200 * 1024;                     // ring budget (barriers + alignment slack on top)
 
@@ -34,7 +37,8 @@ struct Cfg {
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
 template <int BN, bool GEGLU, int CG>
-__global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_constant__ GemmDesc g) {
+__global__ void __launch_bounds__(n_threads(GEGLU), 1) gemm_tc_kernel(const __grid_constant__ GemmDesc g) {
+    constexpr int EW = epi_warps(GEGLU);
     using C = Cfg<BN, CG>;
     const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;      // position in the CTA pair
     const bool leader = rank == 0;
@@ -62,8 +66,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         }
         mbar_init(&tfull[0], 1);
         mbar_init(&tfull[1], 1);
-        mbar_init(&tempty[0], 8 * CG);            // the leader's barrier also collects the peer's 8 epilogue warps
-        mbar_init(&tempty[1], 8 * CG);
+        mbar_init(&tempty[0], EW * CG);           // the leader's barrier also collects the peer's epilogue warps
+        mbar_init(&tempty[1], EW * CG);
         fence_barrier_init();
     }
     if (warp == 1) {                              // 2 accumulator stages x 256 fp32 columns
@@ -204,13 +208,14 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         // interleaved between the two warps of a quadrant.  Per chunk the residual row segment is prefetched one
         // chunk ahead so that HBM/L2 latency overlaps the previous chunk's math and stores.
         const int q = warp & 3;
-        const int hsel = (warp - 2) >> 2;              // which half of the chunks this warp handles
+        const int hsel = (warp - 2) >> 2;              // which share of the chunks this warp handles (EW/4 warps per quadrant)
+        constexpr int CSTEP = EW / 4;
         const int r = q * 32 + lane;                   // row of the tile held by this thread
         int acc = 0;
         uint32_t acc_phase = 0;
         constexpr bool geglu = GEGLU;
         const bool out_f32 = (g.flags & GEMM_OUT_F32) != 0;
-        constexpr int CW = BN >= 32 ? 32 : 16;        // columns per tcgen05.ld
+        constexpr int CW = (BN >= 32 && !GEGLU) ? 32 : 16;        // columns per tcgen05.ld
         constexpr int NV = CW / 8;                     // 16-byte vectors per chunk row segment
         const int ncols_tile = geglu ? BN / 2 : BN;
         const int nchunks = ncols_tile / CW;
@@ -304,10 +309,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
                     bias_s[acc * 256 + et] = bstage;
                     if (ln) csum_s[acc * 256 + et] = cstage;
                 }
-                asm volatile("bar.sync 1, 256;" ::: "memory");     // epilogue warps only (named barrier 1)
+                asm volatile("bar.sync 1, %0;" ::"n"(32 * EW) : "memory");     // epilogue warps only (named barrier 1)
             }
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * 256);
-            for (int ci = hsel; ci < nchunks; ci += 2) {
+            for (int ci = hsel; ci < nchunks; ci += CSTEP) {
                 if (g.flags & GEMM_DBG_NO_EPI) break;
                 const int c0 = ci * CW;
                 uint32_t u[CW];
@@ -321,7 +326,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
                 uint4 rcur[NV];
 #pragma unroll
                 for (int k = 0; k < NV; ++k) rcur[k] = rnext[k];
-                if (ci + 2 < nchunks) prefetch_res(ci + 2);
+                if (ci + CSTEP < nchunks) prefetch_res(ci + CSTEP);
                 const int pcol = tn * BN + c0;                    // packed (accumulator) column of v[0]
                 float bv[CW], bg[CW];
                 if (bias_staged) {
@@ -675,7 +680,7 @@ int gemm_launch(const GemmPlan& plan, cudaStream_t stream) {
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(static_cast<unsigned>(plan.grid));
-    cfg.blockDim = dim3(kThreads);
+    cfg.blockDim = dim3(static_cast<unsigned>(n_threads((plan.desc.flags & GEMM_GEGLU) != 0)));
     cfg.dynamicSmemBytes = static_cast<size_t>(plan.smem);
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
