@@ -5,10 +5,12 @@
 // directly on the channels-last token matrices -- the reference's (b h w) f c / b (h w) c rearranges
 // (t2v_model.py:548-583, :727-761) never materialise.
 //
-// Round-1 implementation: flash-style online softmax with warp-level mma.sync.m16n8k16 (fp16 in, fp32 accumulate,
-// fp32 softmax, P rounded to fp16 for P.V -- the numerics of torch SDPA's fused kernels that the reference
-// dispatches to on sm_100, t2v_model.py:566-569).  QK^T+PV is 3% of the FLOPs at 24f x 256^2;
-// a tcgen05/TMEM version of the S = h*w case is the planned replacement.
+// This file: flash-style online softmax with warp-level mma.sync.m16n8k16 (fp16 in, fp32 accumulate, fp32 softmax,
+// P rounded to fp16 for P.V -- the numerics of torch SDPA's fused kernels that the reference dispatches to on sm_100,
+// t2v_model.py:566-569).  It serves the SHORT sequences: temporal attention (S = frames, 32 x 32 tiles), cross-attention
+// (77 keys) and the coarse levels (h*w < 256).  Long spatial sequences go to the tcgen05 kernel in attention_tc.cu.
+#include <cstdlib>
+
 #include "kernels.cuh"
 #include "ptx.cuh"
 
@@ -200,6 +202,12 @@ __global__ void __launch_bounds__(2 * TS) attention_kernel(AttnParams p) {
 
 int attention(const AttnParams& p, cudaStream_t stream) {
     if (p.head_dim != HD || p.sq <= 0 || p.skv <= 0 || p.kv_batch_div <= 0 || p.b_inner <= 0) return -1;
+    if (attention_tc_eligible(p) && !getenv("T2V_ATTN_WARP_MMA")) {
+        AttnTcPlan plan;
+        const int rc = attention_tc_plan(p, &plan);
+        if (rc != 0) return rc;
+        return attention_tc_launch(plan, stream);
+    }
     const bool small = p.sq <= 32 && p.skv <= 32;
     const int ts = small ? 32 : 64;
     dim3 grid(p.batch, p.heads, (p.sq + ts - 1) / ts);

@@ -538,6 +538,19 @@ int gemm_init() {
     return 0;
 }
 
+int tma_encode_f16(CUtensorMap* m, const void* base, int rank, const unsigned long long* dims,
+                   const unsigned long long* strides_bytes, const unsigned* box) {
+    if (gemm_init() != 0) return -1;
+    cuuint64_t d[5], st[5];
+    cuuint32_t bx[5];
+    for (int i = 0; i < rank; ++i) {
+        d[i] = dims[i];
+        bx[i] = box[i];
+        if (i + 1 < rank) st[i] = strides_bytes[i];
+    }
+    return encode_map(m, base, rank, d, st, bx);
+}
+
 int gemm_plan(const GemmProblem& p, GemmPlan* plan, int num_sms) {
     if (gemm_init() != 0) return -1;
     if (p.nd < 1 || p.nd > GEMM_MAX_RDIMS || p.ntaps < 1 || p.ntaps > GEMM_MAX_TAPS) return -2;

@@ -106,5 +106,8 @@ int gemm_plan(const GemmProblem& p, GemmPlan* plan, int num_sms);
 int gemm_launch(const GemmPlan& plan, cudaStream_t stream);
 // One-time: cudaFuncSetAttribute for all instantiations + driver entry point lookup.
 int gemm_init();
+// fp16 tensor map of rank `rank` with SWIZZLE_128B (box[0] = 64 elements); strides_bytes has rank-1 entries (dims 1..)
+int tma_encode_f16(CUtensorMap* m, const void* base, int rank, const unsigned long long* dims,
+                   const unsigned long long* strides_bytes, const unsigned* box);
 
 }  // namespace t2v

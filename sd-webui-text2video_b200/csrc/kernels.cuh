@@ -1,5 +1,6 @@
 // Declarations of the non-GEMM kernels' host launchers (norm.cu, attention.cu, elementwise.cu).
 #pragma once
+#include <cuda.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stddef.h>
@@ -35,6 +36,19 @@ struct AttnParams {
     float scale;
 };
 int attention(const AttnParams& p, cudaStream_t stream);
+
+// attention_tc.cu: tcgen05 / TMEM / TMA kernel for long self-attention sequences (sq >= 256, skv >= 128, one-level batch).
+// The plan holds the three tensor maps (encoded once per UNet plan, the launch itself is host-side free of driver calls).
+struct AttnTcPlan {
+    CUtensorMap map_q, map_k, map_v;   // rank 3: (heads*64, sequence, batch)
+    __half* o;
+    long long o_bs, o_ss;
+    int sq, skv, kv_batch_div, batch, heads;
+    float sl2;
+};
+bool attention_tc_eligible(const AttnParams& p);
+int attention_tc_plan(const AttnParams& p, AttnTcPlan* plan);
+int attention_tc_launch(const AttnTcPlan& plan, cudaStream_t stream);
 
 // ---------------------------------------------------------------- elementwise.cu
 // x [B, C, F, h, w] (fp32 or fp16, NCFHW as the samplers hold it) -> tokens [B*F*h*w, ld] fp16, channels >= C zeroed up to cpad

@@ -10,6 +10,7 @@
 #include "runtime.cuh"
 
 #include <cmath>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <memory>
@@ -302,9 +303,16 @@ Tok transformer_block(Ctx& c, Tok x, const std::string& p, int heads, int hcur, 
         }
         {
             const AttnParams apc = ap_;
-            c.b->step([apc](cudaStream_t s) { return attention(apc, s); }, 1, STEP_ATTN,
-                      4.0 * apc.batch * apc.heads * static_cast<double>(apc.sq) * apc.skv * 64,
-                      temporal ? "attn temporal" : (self_attn ? "attn spatial" : "attn cross"));
+            const double fl = 4.0 * apc.batch * apc.heads * static_cast<double>(apc.sq) * apc.skv * 64;
+            const char* label = temporal ? "attn temporal" : (self_attn ? "attn spatial" : "attn cross");
+            AttnTcPlan tcp;
+            if (!c.b->dry() && attention_tc_eligible(apc) && !getenv("T2V_ATTN_WARP_MMA") &&
+                attention_tc_plan(apc, &tcp) == 0) {
+                // long sequences: tcgen05 kernel, tensor maps encoded once here
+                c.b->step([tcp](cudaStream_t s) { return attention_tc_launch(tcp, s); }, 1, STEP_ATTN, fl, label);
+            } else {
+                c.b->step([apc](cudaStream_t s) { return attention(apc, s); }, 1, STEP_ATTN, fl, label);
+            }
         }
         c.b->free(qkv);
         if (!self_attn) c.b->free(kv);

@@ -146,6 +146,41 @@ def test_attention_dense_layout(ops, batch, heads, sq, skv):
     assert rel(o, ref) < 3e-3
 
 
+@pytest.mark.parametrize('batch,heads,S', [(2, 5, 1024), (3, 2, 320), (1, 2, 9216), (2, 3, 256), (1, 1, 1000)])
+def test_attention_tcgen05_fused_qkv(ops, batch, heads, S):
+    """Long spatial sequences take the tcgen05/TMEM kernel (csrc/attention_tc.cu): Q, K, V are column slices of the fused
+    [tokens, 3C] matrix, the head is a tensor-map column offset, ragged tails (S % 128 != 0) are TMA zero fill + masking."""
+    C = heads * 64
+    qkv = torch.randn(batch * S, 3 * C, device=dev).half()
+    o = torch.zeros(batch * S, C, device=dev, dtype=torch.half)
+    ld = 3 * C
+    ops.attention(qkv, qkv[:, C:], qkv[:, 2 * C:], o, S * ld, ld, S * ld, ld, S * ld, ld, S * C, C, batch, heads, S, S)
+    t = qkv.float().view(batch, S, 3, heads, 64).permute(2, 0, 3, 1, 4)      # [3, batch, heads, S, 64]
+    ref = F.scaled_dot_product_attention(t[0], t[1], t[2]).permute(0, 2, 1, 3).reshape(batch * S, C)
+    assert rel(o, ref) < 3e-3
+    assert (o.float() - ref).abs().max() < 2e-2
+
+
+def test_attention_tcgen05_shared_kv_and_peaked_scores(ops):
+    """kv_batch_div (frames sharing K/V), skv != sq with a ragged last key tile, and scores large enough that the running
+    max actually moves between key tiles (exercises the exp2 rescale of the running output)."""
+    batch, heads, sq, skv, div = 4, 2, 384, 200, 2
+    C = heads * 64
+    q = (torch.randn(batch, sq, C, device=dev) * 3).half()
+    k = (torch.randn(batch // div, skv, C, device=dev) * 3).half()
+    k[:, 150:] *= 2          # later keys dominate: max rises in the second tile
+    v = torch.randn(batch // div, skv, C, device=dev).half()
+    o = torch.zeros_like(q)
+    ops.attention(q, k, v, o, sq * C, C, skv * C, C, skv * C, C, sq * C, C, batch, heads, sq, skv, kv_batch_div=div)
+
+    def sp(t):
+        return t.float().view(t.shape[0], t.shape[1], heads, 64).permute(0, 2, 1, 3)
+    kk = k.repeat_interleave(div, 0)
+    vv = v.repeat_interleave(div, 0)
+    ref = F.scaled_dot_product_attention(sp(q), sp(kk), sp(vv)).permute(0, 2, 1, 3).reshape(batch, sq, C)
+    assert rel(o, ref) < 3e-3
+
+
 def test_attention_temporal_strides_on_token_matrix(ops):
     """Sequences along frames for every pixel of a [(f, p), 3C] fused qkv matrix -- no rearrange copies."""
     Fr, P, heads = 24, 64, 5
