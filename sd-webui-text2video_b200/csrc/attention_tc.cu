@@ -3,26 +3,33 @@
 //
 // One CTA owns 256 queries (two 128-row tiles) of one (frame, head) and streams the keys/values in 128-row tiles:
 //
-//   warp 8      TMA producer   Q (2 x 16 KB, once), then K_j / V_j tiles into a 3-stage ring -- straight out of the fused
+//   warp 8      TMA producer   Q (2 x 16 KB, once), then K_j / V_j tiles into a 4-stage ring -- straight out of the fused
 //                              [tokens, 3C] QKV matrix: the head is a column offset of the tensor map, rows past the end
 //                              of the frame are TMA zero fill.
-//   warp 9      MMA issuer     S_t = Q_t K_j^T   (4 x tcgen05.mma M128 N128 K16, fp32 in TMEM cols [t*128, +128))
-//                              PV_t = P_t V_j    (8 x tcgen05.mma M128 N64 K16, TMEM cols [256 + t*64, +64)); V is consumed
-//                              as it lies in the token matrix ([key][d] rows) through an MN-major shared-memory descriptor,
-//                              so no transposed copy of V ever exists.
+//   warp 9      MMA issuer     S_t  = Q_t K_j^T  4 x tcgen05.mma M128 N128 K16, both operands from shared memory,
+//                                                fp32 scores in TMEM columns t*128 + [0,128)
+//                              O_t += P_t V_j    8 x tcgen05.mma M128 N64 K16: A = P_t read from TMEM (fp16 pairs, columns
+//                                                256 + t*64 + [0,64)), B = V_j as it lies in the token matrix ([key][d] rows)
+//                                                through an MN-major shared-memory descriptor -- no transposed copy of V, no
+//                                                shared-memory round trip for P; fp32 O_t in TMEM columns 384 + t*64 + [0,64)
 //   warps 0-3   softmax, query tile 0 } thread = query row (TMEM lane): the 128 scores of the row are pulled into registers
-//   warps 4-7   softmax, query tile 1 } in one go (the TMEM copy is released at once, so S_t(j+1) is computed while the
-//                              exponentials of S_t(j) are evaluated), row max, exp2 (MUFU), P -> fp16 -> shared memory in
-//                              the K-major SWIZZLE_128B layout the P.V MMA reads, running output in registers (PV_t is
-//                              double-buffered in TMEM and folded in after P_t(j) has been handed over).
+//   warps 4-7   softmax, query tile 1 } in one go and the TMEM copy released at once (S_t(j+1) is computed while the
+//                              exponentials of S_t(j) are evaluated); row max, exp2 on the MUFU, fp16 pairs stored back
+//                              to TMEM with tcgen05.st.
 //   setmaxnreg moves registers from the TMA/MMA warpgroup (72) to the softmax warpgroups (216).
 //
-// The two query tiles run half an iteration apart: while group 0 evaluates exponentials the tensor core works on
-// S_1 / PV_1 and vice versa; both share every K/V tile (one L2 read per 256 queries).
+// O_t accumulates inside the tensor core across key tiles.  The exponent offset m of a row is therefore only moved
+// (and O_t, l rescaled by exp2((m_old - m_new) c) through a TMEM read-modify-write) when the running max outgrew it by
+// more than 2^8: until then P = exp2(S c - m c) <= 256 is exact in fp16's range and the final O / l is unchanged
+// (every term carries the same factor).  In steady state the softmax warps never touch O_t.
+//
+// The two query tiles run out of phase: while one group evaluates exponentials the tensor core works on the other
+// tile's S / P.V; both share every K/V tile (one L2 read per 256 queries).  Shared-memory traffic per key tile is
+// Q,K operand reads 64 KB + V reads 32 KB + TMA fill 32 KB (128 B/clk/SM), exponentials 32768 / (16/clk/SM).
 //
 // Numerics (= torch SDPA fused kernels the reference dispatches to, t2v_model.py:561-569): fp16 operands, fp32 scores,
-// fp32 online softmax with the scale folded into exp2, P rounded to fp16 for P.V, fp32 output accumulation
-// O = sum_j exp2((m_j - m_final) * c) P_j V_j, normalised by the fp32 row sum at the end.
+// fp32 online softmax with the scale folded into exp2, P rounded to fp16 for P.V, fp32 output accumulation,
+// normalised by the fp32 row sum at the end.
 #include <cuda.h>
 
 #include <cstdio>
@@ -39,20 +46,21 @@ constexpr int HD = 64;
 constexpr int BQ = 128;                 // query rows per tile (= TMEM lanes)
 constexpr int NT = 2;                   // query tiles per CTA
 constexpr int BKV = 128;                // keys per iteration
-constexpr int ST = 3;                   // K/V ring stages
+constexpr int ST = 4;                   // K/V ring stages
 constexpr int TILE_BYTES = 128 * 128;   // 128 rows x 64 fp16
 constexpr int SMEM_Q = 0;
 constexpr int SMEM_K = SMEM_Q + NT * TILE_BYTES;
 constexpr int SMEM_V = SMEM_K + ST * TILE_BYTES;
-constexpr int SMEM_P = SMEM_V + ST * TILE_BYTES;           // per tile: two 64-key atoms of 16 KB
-constexpr int SMEM_BAR = SMEM_P + NT * 2 * TILE_BYTES;
+constexpr int SMEM_BAR = SMEM_V + ST * TILE_BYTES;
 constexpr int SMEM_TOTAL = SMEM_BAR + 256 + 1024;          // + alignment slack
 constexpr int NTHREADS = 384;           // warpgroups: softmax tile 0 | softmax tile 1 | TMA, MMA (+2 idle warps)
 constexpr int REGS_SOFTMAX = 216;       // 2 x 128 x 216 + 128 x 72 = 384 x 168
 constexpr int REGS_OTHER = 72;
 
-constexpr int TMEM_S = 0;               // S_t at columns t*128
-constexpr int TMEM_PV = 256;            // PV_t(j) at columns 256 + t*128 + (j & 1)*64
+constexpr int TMEM_S = 0;               // S_t : fp32 scores, columns t*128 + [0, 128)
+constexpr int TMEM_P = 256;             // P_t : fp16 probabilities, two keys per column, columns 256 + t*64 + [0, 64)
+constexpr int TMEM_O = 384;             // O_t : fp32 running output, columns 384 + t*64 + [0, 64)
+constexpr float RESCALE_LOG2 = 8.f;     // the exponent offset lags the true running max by at most 2^8 (P <= 256 in fp16)
 
 struct Args {
     __half* o;
@@ -60,36 +68,6 @@ struct Args {
     int sq, skv, kv_batch_div, n_kv;
     float sl2;                          // scale * log2(e)
 };
-
-// One softmax iteration's register work on a full row of scores (128 fp32 in s[], destroyed): row max, exponentials,
-// row sum, fp16 packing into pk[64].  MASK: columns >= valid are padding keys.
-template <bool MASK>
-__device__ __forceinline__ void softmax_row(uint32_t (&s)[BKV], uint32_t (&pk)[BKV / 2], int valid, float sl2, float& m_run,
-                                            float& l_run, float& corr) {
-    float mx = m_run;
-#pragma unroll
-    for (int i = 0; i < BKV; i += 2) {
-        if (MASK) {
-            if (i >= valid) s[i] = 0xff800000u;          // -inf
-            if (i + 1 >= valid) s[i + 1] = 0xff800000u;
-        }
-        mx = fmax3(mx, __uint_as_float(s[i]), __uint_as_float(s[i + 1]));
-    }
-    corr = ex2_approx((m_run - mx) * sl2);               // first tile: exp2(-inf) = 0
-    const float msc = mx * sl2;
-    m_run = mx;
-    float sum0 = 0.f, sum1 = 0.f;
-#pragma unroll
-    for (int i = 0; i < BKV; i += 2) {
-        const float p0 = ex2_approx(fmaf(__uint_as_float(s[i]), sl2, -msc));      // exp2(-inf) = 0 for masked keys
-        const float p1 = ex2_approx(fmaf(__uint_as_float(s[i + 1]), sl2, -msc));
-        sum0 += p0;
-        sum1 += p1;
-        const __half2 h = __floats2half2_rn(p0, p1);
-        pk[i >> 1] = *reinterpret_cast<const uint32_t*>(&h);
-    }
-    l_run = fmaf(l_run, corr, sum0 + sum1);
-}
 
 __global__ void __launch_bounds__(NTHREADS, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
@@ -102,8 +80,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
     uint64_t* kv_empty = kv_full + ST;         // [ST] all MMAs reading the stage retired
     uint64_t* s_full = kv_empty + ST;          // [NT] S_t(j) in TMEM
     uint64_t* s_free = s_full + NT;            // [NT] S_t(j) copied to registers: S_t(j+1) may be issued
-    uint64_t* p_full = s_free + NT;            // [NT] P_t(j) in shared memory
-    uint64_t* pv_full = p_full + NT;           // [NT] PV_t(j) in TMEM (P_t buffer and V stage read)
+    uint64_t* p_full = s_free + NT;            // [NT] P_t(j) in TMEM (and O_t rescaled if the row max moved)
+    uint64_t* pv_full = p_full + NT;           // [NT] O_t += P_t(j) V_j retired: P_t may be overwritten, O_t read
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_full + NT);
 
     const int warp = threadIdx.x >> 5;
@@ -161,7 +139,6 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
                 const uint32_t sq_addr = smem_u32(smem + SMEM_Q);
                 const uint32_t sk_addr = smem_u32(smem + SMEM_K);
                 const uint32_t sv_addr = smem_u32(smem + SMEM_V);
-                const uint32_t sp_addr = smem_u32(smem + SMEM_P);
                 auto issue_s = [&](int t, int s) {
                     const uint64_t dq = umma_desc_k_sw128(sq_addr + t * TILE_BYTES);
                     const uint64_t dk = umma_desc_k_sw128(sk_addr + s * TILE_BYTES);
@@ -174,11 +151,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
                     const int s = j % ST;
 #pragma unroll
                     for (int ks = 0; ks < BKV / 16; ++ks) {
-                        // P_t: atom (ks / 4) of 64 keys, 32 B per k-step inside the 128 B row; V: 16 key rows = 2048 B per k-step
-                        const uint64_t dp =
-                            umma_desc_k_sw128(sp_addr + t * 2 * TILE_BYTES + (ks >> 2) * TILE_BYTES) + 2 * (ks & 3);
+                        // A = P_t from TMEM: 16 keys = 8 packed columns per k-step; B = V: 16 key rows = 2048 B per k-step
                         const uint64_t dv = umma_desc_mn_sw128(sv_addr + s * TILE_BYTES + ks * 2048);
-                        umma_f16(tmem_base + TMEM_PV + t * 2 * HD + (j & 1) * HD, dp, dv, idesc_pv, ks > 0);
+                        umma_f16_ts(tmem_base + TMEM_O + t * HD, tmem_base + TMEM_P + t * (BKV / 2) + ks * 8, dv, idesc_pv,
+                                    (j > 0 || ks > 0) ? 1u : 0u);
                     }
                     umma_commit(&pv_full[t]);
                 };
@@ -217,15 +193,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
         const int row = (warp & 3) * 32 + lane;                      // row inside the tile = TMEM lane
         const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
         const uint32_t tS = tmem_base + lane_base + TMEM_S + t * BKV;
-        const uint32_t tPV = tmem_base + lane_base + TMEM_PV + t * 2 * HD;
-        const uint32_t p_row = smem_u32(smem + SMEM_P + t * 2 * TILE_BYTES) + row * 128;
-        const int sw = row & 7;
+        const uint32_t tP = tmem_base + lane_base + TMEM_P + t * (BKV / 2);
+        const uint32_t tO = tmem_base + lane_base + TMEM_O + t * HD;
         const float sl2 = a.sl2;
-
-        float o[HD];
-#pragma unroll
-        for (int i = 0; i < HD; ++i) o[i] = 0.f;
-        float m_run = -INFINITY, l_run = 0.f, corr_prev = 0.f;
+        if (t == 1) named_bar_arrive(2, 2 * BQ);             // MUFU turn-taking: group 0 goes first
+        float m_used = -INFINITY;        // exponent offset in use (<= true running max, lags it by at most RESCALE_LOG2)
+        float l_run = 0.f;
 
         for (int j = 0; j < n_kv; ++j) {
             const int valid = a.skv - j * BKV;                       // >= BKV: the whole tile is real keys
@@ -239,35 +212,74 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
             __syncwarp();
             if (lane == 0) mbar_arrive(&s_free[t]);                  // S_t(j+1) may overwrite the TMEM copy now
 
-            uint32_t pk[BKV / 2];
-            float corr;
-            if (valid >= BKV) softmax_row<false>(s, pk, valid, sl2, m_run, l_run, corr);
-            else softmax_row<true>(s, pk, valid, sl2, m_run, l_run, corr);
-
-            // P_t(j-1) has been consumed once PV_t(j-1) retired: overwrite the buffer (K-major, 128 B swizzle)
-            if (j > 0) mbar_wait(&pv_full[t], (j - 1) & 1);
+            // ---- row max (padding keys of a ragged last tile -> -inf); four independent chains
+            if (valid < BKV) {
 #pragma unroll
-            for (int chunk = 0; chunk < BKV / 8; ++chunk) {          // 16 B chunk = 8 keys; atom = chunk / 8
-                const uint32_t addr = p_row + (chunk >> 3) * TILE_BYTES + (((chunk & 7) ^ sw) << 4);
-                sts_128(addr, pk[chunk * 4 + 0], pk[chunk * 4 + 1], pk[chunk * 4 + 2], pk[chunk * 4 + 3]);
+                for (int i = 0; i < BKV; ++i)
+                    if (i >= valid) s[i] = 0xff800000u;
             }
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&p_full[t]);
-            // fold PV_t(j-1) into the running output while the tensor core works on P_t(j)
-            if (j > 0) {
+            float mx4[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                mx4[c] = fmaxf(__uint_as_float(s[c * 32]), __uint_as_float(s[c * 32 + 1]));
+#pragma unroll
+                for (int i = 2; i < 32; i += 2)
+                    mx4[c] = fmax3(mx4[c], __uint_as_float(s[c * 32 + i]), __uint_as_float(s[c * 32 + i + 1]));
+            }
+            const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+
+            // ---- move the exponent offset only when the row max outgrew it by 2^RESCALE_LOG2 (warp-uniform decision:
+            //      the TMEM accesses are warp-collective); rescaling a row that did not need it is exact (corr <= 1)
+            if (j == 0) {
+                m_used = mx;
+            } else if (__any_sync(0xffffffffu, (mx - m_used) * sl2 > RESCALE_LOG2)) {
+                mbar_wait(&pv_full[t], (j - 1) & 1);                 // O_t quiescent once PV_t(j-1) retired
                 tc_fence_after();
+                const float m_new = fmaxf(m_used, mx);
+                const float corr = ex2_approx((m_used - m_new) * sl2);
+                m_used = m_new;
+                l_run *= corr;
                 uint32_t r[HD];
-                tmem_ld_32x32_p(tPV + ((j - 1) & 1) * HD, r);
-                tmem_ld_32x32_p(tPV + ((j - 1) & 1) * HD + 32, r + 32);
+                tmem_ld_32x32_p(tO, r);
+                tmem_ld_32x32_p(tO + 32, r + 32);
                 tmem_ld_wait();
 #pragma unroll
-                for (int i = 0; i < HD; ++i) o[i] = fmaf(o[i], corr_prev, __uint_as_float(r[i]));
-                tc_fence_before();
+                for (int i = 0; i < HD; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * corr);
+                tmem_st_32x32_p(tO, r);
+                tmem_st_32x32_p(tO + 32, r + 32);
             }
-            corr_prev = corr;
+            // ---- P = exp2(S * c - m * c) -> fp16 pairs -> TMEM (A operand of the P.V MMA).  The MUFU is the scarcest unit
+            //      of the whole kernel (16 exp2/clk/SM): the two softmax groups take turns on it, so that one group's
+            //      loads / max / stores always run under the other group's exponentials instead of both stalling on it.
+            const float msc = m_used * sl2;
+            float sum0 = 0.f, sum1 = 0.f;
+            named_bar_sync(2 + t, 2 * BQ);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                uint32_t pk[BKV / 4];
+#pragma unroll
+                for (int i = 0; i < BKV / 2; i += 2) {
+                    const float p0 = ex2_approx(fmaf(__uint_as_float(s[h * 64 + i]), sl2, -msc));    // exp2(-inf) = 0
+                    const float p1 = ex2_approx(fmaf(__uint_as_float(s[h * 64 + i + 1]), sl2, -msc));
+                    sum0 += p0;
+                    sum1 += p1;
+                    const __half2 hh = __floats2half2_rn(p0, p1);
+                    pk[i >> 1] = *reinterpret_cast<const uint32_t*>(&hh);
+                }
+                if (h == 0 && j > 0) {                               // P_t(j-1) consumed once PV_t(j-1) retired
+                    mbar_wait(&pv_full[t], (j - 1) & 1);
+                    tc_fence_after();
+                }
+                if (h == 1 && !(t == 1 && j == n_kv - 1)) named_bar_arrive(2 + (t ^ 1), 2 * BQ);   // hand the MUFU over
+                tmem_st_32x32_p(tP + h * 32, pk);
+            }
+            l_run += sum0 + sum1;
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&p_full[t]);
         }
-        // ---- last tile's P.V, normalise, store
+        // ---- normalise, store
         mbar_wait(&pv_full[t], (n_kv - 1) & 1);
         tc_fence_after();
         const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
@@ -276,14 +288,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
 #pragma unroll
         for (int c = 0; c < HD / 32; ++c) {
             uint32_t r[32];
-            tmem_ld_32x32(tPV + ((n_kv - 1) & 1) * HD + c * 32, r);
+            tmem_ld_32x32(tO + c * 32, r);
             tmem_ld_wait();
             uint32_t w[16];
 #pragma unroll
             for (int i = 0; i < 32; i += 2) {
-                const float v0 = fmaf(o[c * 32 + i], corr_prev, __uint_as_float(r[i])) * inv;
-                const float v1 = fmaf(o[c * 32 + i + 1], corr_prev, __uint_as_float(r[i + 1])) * inv;
-                const __half2 h = __floats2half2_rn(v0, v1);
+                const __half2 h = __floats2half2_rn(__uint_as_float(r[i]) * inv, __uint_as_float(r[i + 1]) * inv);
                 w[i >> 1] = *reinterpret_cast<const uint32_t*>(&h);
             }
             if (qrow < a.sq) {

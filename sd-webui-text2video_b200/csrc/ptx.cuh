@@ -219,6 +219,13 @@ __device__ __forceinline__ void tmem_ld_32x32_p(uint32_t taddr, uint32_t* r) {
         : "r"(taddr)
         : "memory");
 }
+// named barriers: `sync` blocks until `count` threads have arrived (sync or arrive) on barrier `id`
+__device__ __forceinline__ void named_bar_sync(int id, int count) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+__device__ __forceinline__ void named_bar_arrive(int id, int count) {
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
 // warpgroup-wide register re-budgeting (all 4 warps of the warpgroup execute it)
 template <int N>
 __device__ __forceinline__ void setmaxnreg_inc() {
