@@ -31,7 +31,13 @@ def bench(M, K, N, bn, flags=0, res=False, bias=True, cg=1, taps=None, dims=None
     fl = 2.0 * M * N * K * nt
     return cold * 1e3, warm * 1e3, fl / warm / 1e9
 NS, NE, NM = 256, 512, 1024
-for (M, K, N, bn) in ((49152, 320, 320, 160), (49152, 320, 960, 160), (49152, 320, 960, 256), (49152, 320, 320, 64), (49152, 320, 320, 128), (12288, 640, 640, 160)):
+GEGLU = 1
+cases = [(49152, 320, 320, 160, 0), (49152, 320, 2560, 256, GEGLU), (12288, 640, 5120, 256, GEGLU), (49152, 320, 960, 256, 0)]
+if len(sys.argv) > 1:
+    cases = [c for c in cases if str(c[2]) in sys.argv[1:]]
+for (M, K, N, bn, base) in cases:
     for name, fl, res in (('full+res', 0, True), ('full', 0, False), ('no_store', NS, False), ('no_epilogue', NE, False), ('no_mma', NM, False), ('no_mma_no_epi', NM | NE, False)):
-        c, w_, tf = bench(M, K, N, bn, flags=fl, res=res)
-        print(f'M{M} K{K} N{N} bn{bn} {name:14s}: cold {c:7.1f} us  warm {w_:7.1f} us  ({tf:6.1f} TF/s warm)', flush=True)
+        if base and res:
+            continue
+        c, w_, tf = bench(M, K, N, bn, flags=fl | base, res=res)
+        print(f'M{M} K{K} N{N} bn{bn} {"geglu " if base else ""}{name:14s}: cold {c:7.1f} us  warm {w_:7.1f} us  ({tf:6.1f} TF/s warm)', flush=True)

@@ -19,9 +19,14 @@ namespace t2v {
 
 namespace {
 
-// TMA warp + MMA warp + EW epilogue warps.  EW = 8 normally; the GEGLU epilogue (erf, three fp16 rounding points per
-// element) is issue/latency bound at small K, so it runs 16 warps on 16-column chunks (register budget 65536/576 = 113).
-constexpr int epi_warps(bool geglu) { return geglu ? 16 : 8; }
+// TMA warp + MMA warp + EW epilogue warps (8: two per TMEM lane quadrant).  The GEGLU epilogue has its own lean loop
+// (A&S erfc-form GELU on MUFU, paired fp16 conversions, HMUL2 product, no residual / scalar fallbacks): with the generic
+// path and erff() it was capped at 96 registers with spills and ran at 364 TFLOP/s on the level-0 FF (K = 320); the
+// dedicated loop reaches 740 (profiles/r01_gemm_isolation.txt).  -DT2V_GEGLU_EW=16 builds the 16-warp / 16-column variant.
+#ifndef T2V_GEGLU_EW
+#define T2V_GEGLU_EW 8
+#endif
+constexpr int epi_warps(bool geglu) { return geglu ? T2V_GEGLU_EW : 8; }
 constexpr int n_threads(bool geglu) { return 64 + 32 * epi_warps(geglu); }
 constexpr int kABytes = GEMM_BLOCK_M * GEMM_BLOCK_K * 2;   // 16 KB
 constexpr int kSmemBudget = 200 * 1024;                     // ring budget (barriers + alignment slack on top)
@@ -34,7 +39,21 @@ struct Cfg {
     static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + 4096 /*bias + colsum tiles*/;
 };
 
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+// erf-form GELU x * Phi(x) (F.gelu default, t2v_model.py:821).  Phi(x) = 1/2 erfc(-x / sqrt 2); for z = |x| / sqrt 2
+// erfc(z) = t (a1 + t (a2 + t (a3 + t (a4 + t a5)))) exp(-z^2), t = 1 / (1 + p z) (Abramowitz-Stegun 7.1.26, |error| <=
+// 1.5e-7 -- three orders below the fp16 rounding the reference applies to the result).  2 MUFU (rcp, ex2) + 13 FMA-pipe
+// instructions instead of erff's ~32: the GEGLU epilogue is instruction-issue bound at K = 320.
+__device__ __forceinline__ float gelu_erf(float x) {
+    const float z = fabsf(x) * 0.70710678118654752440f;
+    float t;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
+    float p = fmaf(t, 0.5f * 1.061405429f, 0.5f * -1.453152027f);
+    p = fmaf(p, t, 0.5f * 1.421413741f);
+    p = fmaf(p, t, 0.5f * -0.284496736f);
+    p = fmaf(p, t, 0.5f * 0.254829592f);
+    const float q = p * t * ex2_approx(z * z * -1.4426950408889634f);      // 1/2 erfc(z)
+    return x * (x < 0.f ? q : 1.0f - q);
+}
 
 template <int BN, bool GEGLU, int CG>
 __global__ void __launch_bounds__(n_threads(GEGLU), 1) gemm_tc_kernel(const __grid_constant__ GemmDesc g) {
@@ -215,7 +234,7 @@ __global__ void __launch_bounds__(n_threads(GEGLU), 1) gemm_tc_kernel(const __gr
         uint32_t acc_phase = 0;
         constexpr bool geglu = GEGLU;
         const bool out_f32 = (g.flags & GEMM_OUT_F32) != 0;
-        constexpr int CW = (BN >= 32 && !GEGLU) ? 32 : 16;        // columns per tcgen05.ld
+        constexpr int CW = (BN >= 32 && (!GEGLU || EW == 8)) ? 32 : 16;        // columns per tcgen05.ld
         constexpr int NV = CW / 8;                     // 16-byte vectors per chunk row segment
         const int ncols_tile = geglu ? BN / 2 : BN;
         const int nchunks = ncols_tile / CW;
@@ -223,13 +242,13 @@ __global__ void __launch_bounds__(n_threads(GEGLU), 1) gemm_tc_kernel(const __gr
         const bool vec_ok = ((g.ldo & 7) == 0) && ((g.N & 7) == 0) && (!geglu || (g.N & 15) == 0) &&
                             (g.residual == nullptr || (g.ldr & 7) == 0);
         // 32-byte (one full sector per thread) stores / residual loads when every row segment is 32 B aligned
-        const bool vec32 = vec_ok && !out_f32 && (CW == 32) && ((g.ldo & 15) == 0) && ((nvalid & 15) == 0) &&
+        const bool vec32 = vec_ok && !out_f32 && ((g.ldo & 15) == 0) && ((nvalid & 15) == 0) &&
                            ((reinterpret_cast<uintptr_t>(g.out) & 31) == 0) &&
                            (g.residual == nullptr || (((g.ldr & 15) == 0) && ((reinterpret_cast<uintptr_t>(g.residual) & 31) == 0)));
         // A bias shared by all rows is staged once per tile in smem (its L2 latency hides behind the wait for the
         // accumulator); per-sample bias rows (time-embedding add of the ResBlock convs) are read per thread.
         const bool ln = (g.flags & GEMM_LN) != 0;
-        const bool bias_staged = ln || ((g.bias != nullptr) && (g.bias_rows == 0));
+        const bool bias_staged = GEGLU || ln || ((g.bias != nullptr) && (g.bias_rows == 0));   // GEGLU: always (zeros if no bias)
         const int et = static_cast<int>(threadIdx.x) - 64;       // 0..255 among the epilogue threads
         for (int wi = first_pair; wi < total_pairs; wi += pair_stride) {
             const int sp = wi % nsplit;
@@ -284,7 +303,7 @@ __global__ void __launch_bounds__(n_threads(GEGLU), 1) gemm_tc_kernel(const __gr
                     }
                 }
             };
-            if (hsel < nchunks) prefetch_res(hsel);
+            if constexpr (!GEGLU) { if (hsel < nchunks) prefetch_res(hsel); }
             float bstage = 0.f, cstage = 0.f;
             if (bias_staged && et < BN) {
                 const int col = tn * BN + et;
@@ -292,7 +311,7 @@ __global__ void __launch_bounds__(n_threads(GEGLU), 1) gemm_tc_kernel(const __gr
                     if (ln) {
                         bstage = __ldg(g.bias32 + col);
                         cstage = __ldg(g.colsum + col);
-                    } else {
+                    } else if (g.bias != nullptr) {
                         bstage = __half2float(__ldg(g.bias + col));
                     }
                 }
@@ -323,27 +342,63 @@ __global__ void __launch_bounds__(n_threads(GEGLU), 1) gemm_tc_kernel(const __gr
                     if constexpr (CW == 32) tmem_ld_32x32(taddr + BN / 2 + c0, ug);
                     else tmem_ld_32x16(taddr + BN / 2 + c0, ug);
                 }
+                if constexpr (GEGLU) {
+                    // GEGLU tile: out = fp16(value) * fp16(gelu(fp16(gate))) with the reference's fp16 rounding points
+                    // (t2v_model.py:819-821 under autocast: proj output, gelu output, product).  Bias / LayerNorm-fold
+                    // vectors come from the staged smem tile, no residual, 32 B aligned fp16 rows (gemm_plan checks).
+                    tmem_ld_wait();
+                    uint32_t ow[CW / 2];
+#pragma unroll
+                    for (int j = 0; j < CW; j += 2) {
+                        const float2 bx = *reinterpret_cast<const float2*>(bs + c0 + j);
+                        const float2 bgt = *reinterpret_cast<const float2*>(bs + BN / 2 + c0 + j);
+                        float x0, x1, g0, g1;
+                        if (ln) {
+                            const float2 cx = *reinterpret_cast<const float2*>(cs + c0 + j);
+                            const float2 cg = *reinterpret_cast<const float2*>(cs + BN / 2 + c0 + j);
+                            x0 = fmaf(rs.y, fmaf(-rs.x, cx.x, __uint_as_float(u[j])), bx.x);
+                            x1 = fmaf(rs.y, fmaf(-rs.x, cx.y, __uint_as_float(u[j + 1])), bx.y);
+                            g0 = fmaf(rs.y, fmaf(-rs.x, cg.x, __uint_as_float(ug[j])), bgt.x);
+                            g1 = fmaf(rs.y, fmaf(-rs.x, cg.y, __uint_as_float(ug[j + 1])), bgt.y);
+                        } else {
+                            x0 = fmaf(__uint_as_float(u[j]), g.alpha, bx.x);
+                            x1 = fmaf(__uint_as_float(u[j + 1]), g.alpha, bx.y);
+                            g0 = fmaf(__uint_as_float(ug[j]), g.alpha, bgt.x);
+                            g1 = fmaf(__uint_as_float(ug[j + 1]), g.alpha, bgt.y);
+                        }
+                        const __half2 xh = __floats2half2_rn(x0, x1);
+                        const float2 gf = __half22float2(__floats2half2_rn(g0, g1));
+                        const __half2 ge = __floats2half2_rn(gelu_erf(gf.x), gelu_erf(gf.y));
+                        const __half2 oh = __hmul2(xh, ge);            // fp16 x fp16 -> fp16 (RN) == the reference's product
+                        ow[j >> 1] = *reinterpret_cast<const uint32_t*>(&oh);
+                    }
+                    if (valid && !(g.flags & GEMM_DBG_NO_STORE)) {
+                        __half* op = reinterpret_cast<__half*>(g.out) + grow * g.ldo + ocol0 + c0;
+#pragma unroll
+                        for (int k = 0; k < CW / 16; ++k) {
+                            U32x8 ov;
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) ov.v[e] = ow[k * 8 + e];
+                            stg_256(op + k * 16, ov);
+                        }
+                    }
+                } else {
                 uint4 rcur[NV];
 #pragma unroll
                 for (int k = 0; k < NV; ++k) rcur[k] = rnext[k];
                 if (ci + CSTEP < nchunks) prefetch_res(ci + CSTEP);
                 const int pcol = tn * BN + c0;                    // packed (accumulator) column of v[0]
-                float bv[CW], bg[CW];
+                float bv[CW];
                 if (bias_staged) {
 #pragma unroll
                     for (int j = 0; j < CW; j += 4) {
                         const float4 t4 = *reinterpret_cast<const float4*>(bs + c0 + j);       // smem broadcast
                         bv[j] = t4.x; bv[j + 1] = t4.y; bv[j + 2] = t4.z; bv[j + 3] = t4.w;
-                        if (geglu) {
-                            const float4 g4 = *reinterpret_cast<const float4*>(bs + BN / 2 + c0 + j);
-                            bg[j] = g4.x; bg[j + 1] = g4.y; bg[j + 2] = g4.z; bg[j + 3] = g4.w;
-                        }
                     }
                 } else {
 #pragma unroll
                     for (int j = 0; j < CW; ++j) {
                         bv[j] = (bias != nullptr && pcol + j < g.N) ? __half2float(__ldg(bias + pcol + j)) : 0.f;
-                        bg[j] = (geglu && bias != nullptr && pcol + BN / 2 + j < g.N) ? __half2float(__ldg(bias + pcol + BN / 2 + j)) : 0.f;
                     }
                 }
                 tmem_ld_wait();
@@ -354,18 +409,6 @@ __global__ void __launch_bounds__(n_threads(GEGLU), 1) gemm_tc_kernel(const __gr
                 } else {
 #pragma unroll
                     for (int j = 0; j < CW; ++j) v[j] = fmaf(__uint_as_float(u[j]), g.alpha, bv[j]);
-                }
-                if (geglu) {
-#pragma unroll
-                    for (int j = 0; j < CW; ++j) {
-                        const float gt = ln ? fmaf(rs.y, fmaf(-rs.x, cs[BN / 2 + c0 + j], __uint_as_float(ug[j])), bg[j])
-                                            : fmaf(__uint_as_float(ug[j]), g.alpha, bg[j]);
-                        // reference rounding points (fp16 autocast): proj output, gelu output, product
-                        const float xa = __half2float(__float2half_rn(v[j]));
-                        const float ga = __half2float(__float2half_rn(gt));
-                        const float ge = __half2float(__float2half_rn(gelu_erf(ga)));
-                        v[j] = xa * ge;
-                    }
                 }
                 const int ocol = ocol0 + c0;
                 if (valid && !(g.flags & GEMM_DBG_NO_STORE)) {
@@ -440,6 +483,7 @@ __global__ void __launch_bounds__(n_threads(GEGLU), 1) gemm_tc_kernel(const __gr
                         }
                     }
                 }
+                }   // !GEGLU
             }
             tc_fence_before();
             __syncwarp();
@@ -648,6 +692,12 @@ int gemm_plan(const GemmProblem& p, GemmPlan* plan, int num_sms) {
     g.tiles_n = (p.N + bn - 1) / bn;
     if ((p.flags & GEMM_GEGLU) && (p.N % bn) != 0) {
         fprintf(stderr, "[t2v_b200] gemm_plan: GEGLU needs N %% BN == 0 (N %d BN %d)\n", p.N, bn);
+        return -4;
+    }
+    if ((p.flags & GEMM_GEGLU) && ((p.ldo & 15) != 0 || (reinterpret_cast<uintptr_t>(p.out) & 31) != 0 || p.residual != nullptr ||
+                                   (p.flags & GEMM_OUT_F32) || p.bias_rows != 0 || p.splits > 1)) {
+        fprintf(stderr, "[t2v_b200] gemm_plan: GEGLU epilogue needs 32-byte aligned fp16 output rows (ldo %lld), no residual, "
+                        "no per-sample bias, no split-K\n", p.ldo);
         return -4;
     }
 

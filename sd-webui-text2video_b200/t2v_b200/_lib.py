@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libt2v_b200.so')
+LIB_PATH = os.environ.get('T2V_LIB_PATH') or os.path.join(_HERE, 'libt2v_b200.so')      # override: A/B builds of the kernels
 
 c_void_p, c_int, c_ll, c_float, c_char_p, c_double = C.c_void_p, C.c_int, C.c_longlong, C.c_float, C.c_char_p, C.c_double
 P = c_void_p
