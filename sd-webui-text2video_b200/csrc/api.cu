@@ -5,6 +5,7 @@
 #include "kernels.cuh"
 
 #include <cstdarg>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 
@@ -23,6 +24,10 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 int num_sms() { return g_num_sms; }
+bool pdl_enabled() {
+    static const bool on = getenv("T2V_PDL") != nullptr;      // opt-in: measured 2.7 % SLOWER on the graphed forward
+    return on;
+}
 
 static void* gn_scratch(size_t bytes) {
     if (bytes > g_gn_ws_bytes) {

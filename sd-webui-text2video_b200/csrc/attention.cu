@@ -11,6 +11,7 @@
 // (77 keys) and the coarse levels (h*w < 256).  Long spatial sequences go to the tcgen05 kernel in attention_tc.cu.
 #include <cstdlib>
 
+#include "common.cuh"
 #include "kernels.cuh"
 #include "ptx.cuh"
 
@@ -42,6 +43,8 @@ __device__ __forceinline__ void load_tile(uint32_t smem_tile, const __half* gbas
 
 template <int TS>
 __global__ void __launch_bounds__(2 * TS) attention_kernel(AttnParams p) {
+    griddep_wait();
+    griddep_launch_small();
     constexpr int BM = TS, BNK = TS, NB = TS / 8, KS = TS / 16, TB = TS * 128;   // tile bytes
     __shared__ __align__(128) uint8_t smem[TB * 5];   // Q | K0 | K1 | V0 | V1
     const uint32_t sQ = smem_u32(smem);
@@ -212,8 +215,8 @@ int attention(const AttnParams& p, cudaStream_t stream) {
     const int ts = small ? 32 : 64;
     dim3 grid(p.batch, p.heads, (p.sq + ts - 1) / ts);
     if (grid.z > 65535 || grid.y > 65535) return -3;
-    if (small) attention_kernel<32><<<grid, 64, 0, stream>>>(p);
-    else attention_kernel<64><<<grid, 128, 0, stream>>>(p);
+    if (small) launch_pdl(attention_kernel<32>, grid, 64, 0, stream, p);
+    else launch_pdl(attention_kernel<64>, grid, 128, 0, stream, p);
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 

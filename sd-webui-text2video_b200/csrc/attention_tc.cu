@@ -35,6 +35,7 @@
 #include <cstdio>
 
 #include "gemm_tc.cuh"
+#include "common.cuh"
 #include "kernels.cuh"
 #include "ptx.cuh"
 
@@ -110,6 +111,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    griddep_wait();        // the prologue above overlaps the previous kernel's tail (PDL, common.cuh)
 
     if (warp >= 8) {
         setmaxnreg_dec<REGS_OTHER>();
@@ -130,6 +132,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
                     tma_load_3d(smem + SMEM_K + s * TILE_BYTES, &map_k, &kv_full[s], head * HD, j * BKV, bkv);
                     tma_load_3d(smem + SMEM_V + s * TILE_BYTES, &map_v, &kv_full[s], head * HD, j * BKV, bkv);
                 }
+                griddep_launch();          // all loads issued: dependents may be scheduled as SMs drain
             }
         } else if (warp == 9) {
             // -------------------------------------------------------------- MMA issuer
@@ -383,7 +386,7 @@ int attention_tc_launch(const AttnTcPlan& pl, cudaStream_t stream) {
     a.n_kv = (pl.skv + BKV - 1) / BKV;
     a.sl2 = pl.sl2;
     dim3 grid((pl.sq + NT * BQ - 1) / (NT * BQ), pl.heads, pl.batch);
-    attention_tc_kernel<<<grid, NTHREADS, SMEM_TOTAL, stream>>>(pl.map_q, pl.map_k, pl.map_v, a);
+    launch_pdl(attention_tc_kernel, grid, NTHREADS, SMEM_TOTAL, stream, pl.map_q, pl.map_k, pl.map_v, a);
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 

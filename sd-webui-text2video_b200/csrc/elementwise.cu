@@ -1,6 +1,7 @@
 // HBM-bound glue kernels: layout ingest/egress, nearest-2x upsample, stride-2 gather, concat, time embedding,
 // tiny-M linears, row softmax, transposes, uint8 frame conversion, weight packing, sampler updates.
 // All are simple grid-stride kernels with 16-byte vector accesses where the layout allows.
+#include "common.cuh"
 #include "kernels.cuh"
 
 #include <math_constants.h>
@@ -21,6 +22,8 @@ inline int grid_for(long long n, int threads, int cap = 148 * 16) {
 
 __global__ void ingest_kernel(const void* x, int x_is_f32, __half* tok, long long ld, int cpad, int B, int C, int F,
                               int h, int w, float scale) {
+    griddep_wait();
+    griddep_launch_small();
     const long long P = static_cast<long long>(h) * w;
     const long long rows = static_cast<long long>(B) * F * P;
     GRID_STRIDE(i, rows * cpad) {
@@ -42,6 +45,8 @@ __global__ void ingest_kernel(const void* x, int x_is_f32, __half* tok, long lon
 
 __global__ void egress_kernel(const __half* tok, long long ld, void* out, int out_is_f32, int B, int C, int F, int h,
                               int w) {
+    griddep_wait();
+    griddep_launch_small();
     const long long P = static_cast<long long>(h) * w;
     const long long n = static_cast<long long>(B) * C * F * P;
     GRID_STRIDE(i, n) {
@@ -58,6 +63,8 @@ __global__ void egress_kernel(const __half* tok, long long ld, void* out, int ou
 }
 
 __global__ void upsample2x_kernel(const uint4* x, uint4* y, long long nframes, int h, int w, int C8) {
+    griddep_wait();
+    griddep_launch_small();
     const int H = 2 * h, W = 2 * w;
     const long long n = nframes * H * W * C8;
     GRID_STRIDE(i, n) {
@@ -72,6 +79,8 @@ __global__ void upsample2x_kernel(const uint4* x, uint4* y, long long nframes, i
 }
 
 __global__ void im2col_s2_kernel(const uint4* x, uint4* col, long long nframes, int h, int w, int C8) {
+    griddep_wait();
+    griddep_launch_small();
     const int ho = (h + 1) / 2, wo = (w + 1) / 2;      // floor((h + 2 - 3)/2) + 1
     const long long n = nframes * ho * wo * 9 * C8;
     GRID_STRIDE(i, n) {
@@ -93,6 +102,8 @@ __global__ void im2col_s2_kernel(const uint4* x, uint4* col, long long nframes, 
 
 __global__ void concat_kernel(const __half* a, long long lda, int Ca8, const __half* b, long long ldb, int Cb8,
                               __half* out, long long ldo, long long rows) {
+    griddep_wait();
+    griddep_launch_small();
     const int T8 = Ca8 + Cb8;
     GRID_STRIDE(i, rows * T8) {
         const long long r = i / T8;
@@ -105,6 +116,8 @@ __global__ void concat_kernel(const __half* a, long long lda, int Ca8, const __h
 }
 
 __global__ void time_sinusoid_kernel(const float* t, __half* out, int B, int dim) {
+    griddep_wait();
+    griddep_launch_small();
     const int half_dim = dim / 2;
     GRID_STRIDE(i, static_cast<long long>(B) * dim) {
         const int b = static_cast<int>(i / dim);
@@ -125,6 +138,8 @@ __global__ void time_sinusoid_kernel(const float* t, __half* out, int B, int dim
 __global__ void __launch_bounds__(256) small_linear_kernel(const __half* x, long long ldx, const __half* W,
                                                            const __half* bias, const __half* addend, __half* y,
                                                            long long ldy, int B, int N, int K, int silu_in) {
+    griddep_wait();
+    griddep_launch_small();
     const int lane = threadIdx.x & 31;
     const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (n >= N) return;
@@ -156,6 +171,8 @@ __global__ void __launch_bounds__(256) small_linear_kernel(const __half* x, long
 
 __global__ void __launch_bounds__(256) softmax_rows_kernel(const __half* x, __half* y, long long rows, int cols,
                                                            float scale) {
+    griddep_wait();
+    griddep_launch_small();
     // one warp per row, fp32 math; the scaled logits are rounded to fp16 first (reference: w_ * c^-0.5 in fp16)
     const int lane = threadIdx.x & 31;
     const long long row = blockIdx.x * static_cast<long long>(blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -176,6 +193,8 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(const __half* x, __ha
 }
 
 __global__ void transpose_kernel(const __half* x, __half* y, int R, int C) {
+    griddep_wait();
+    griddep_launch_small();
     __shared__ __half tile[32][34];
     const long long base = static_cast<long long>(blockIdx.z) * R * C;
     const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
@@ -191,6 +210,8 @@ __global__ void transpose_kernel(const __half* x, __half* y, int R, int C) {
 }
 
 __global__ void frames_to_u8_kernel(const __half* tok, long long ld, uint8_t* out, long long pixels) {
+    griddep_wait();
+    griddep_launch_small();
     GRID_STRIDE(i, pixels * 3) {
         const long long p = i / 3;
         const int c = static_cast<int>(i - p * 3);
@@ -203,6 +224,8 @@ __global__ void frames_to_u8_kernel(const __half* tok, long long ld, uint8_t* ou
 }
 
 __global__ void frames_to_f32_kernel(const __half* tok, long long ld, float* out, int n, int H, int W) {
+    griddep_wait();
+    griddep_launch_small();
     const long long P = static_cast<long long>(H) * W;
     GRID_STRIDE(i, static_cast<long long>(n) * 3 * P) {
         const long long p = i % P;
@@ -215,6 +238,8 @@ __global__ void frames_to_f32_kernel(const __half* tok, long long ld, float* out
 
 __global__ void pack_conv_kernel(const void* src, int src_is_f32, __half* dst, int Cout, int Cin, int taps, int n_alloc,
                                  int k_alloc) {
+    griddep_wait();
+    griddep_launch_small();
     const long long n = static_cast<long long>(taps) * n_alloc * k_alloc;
     GRID_STRIDE(i, n) {
         const int k = static_cast<int>(i % k_alloc);
@@ -232,6 +257,8 @@ __global__ void pack_conv_kernel(const void* src, int src_is_f32, __half* dst, i
 
 __global__ void pack_geglu_kernel(const void* w, const void* b, int src_is_f32, __half* wdst, __half* bdst, int H, int K,
                                   int bn) {
+    griddep_wait();
+    griddep_launch_small();
     // packed row p: tile = p / bn, j = p % bn ; j < bn/2 -> value channel tile*bn/2 + j ; else gate channel H + tile*bn/2 + (j - bn/2)
     const long long n = static_cast<long long>(2) * H * K;
     const int hb = bn / 2;
@@ -252,6 +279,8 @@ __global__ void pack_geglu_kernel(const void* w, const void* b, int src_is_f32, 
 __global__ void splitk_reduce_kernel(const float* part, int splits, long long split_stride, long long rows, int N8,
                                      const __half* bias, int bias_rows, long long bias_stride, const __half* residual,
                                      long long ldr, __half* out, long long ldo) {
+    griddep_wait();
+    griddep_launch_small();
     GRID_STRIDE(i, rows * N8) {
         const long long r = i / N8;
         const int c = static_cast<int>(i - r * N8) * 8;
@@ -288,6 +317,8 @@ __global__ void splitk_reduce_kernel(const float* part, int splits, long long sp
 // one warp per output row n
 __global__ void __launch_bounds__(256) fold_ln_kernel(const __half* w, const __half* bias, const __half* gamma, const __half* beta,
                                                       __half* wout, float* colsum, float* bias32, int N, int K) {
+    griddep_wait();
+    griddep_launch_small();
     const int lane = threadIdx.x & 31;
     const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (n >= N) return;
@@ -311,6 +342,8 @@ __global__ void __launch_bounds__(256) fold_ln_kernel(const __half* w, const __h
 }
 
 __global__ void convert_kernel(const void* src, int src_is_f32, __half* dst, long long n) {
+    griddep_wait();
+    griddep_launch_small();
     GRID_STRIDE(i, n) {
         dst[i] = src_is_f32 ? __float2half_rn(reinterpret_cast<const float*>(src)[i]) : reinterpret_cast<const __half*>(src)[i];
     }
@@ -331,6 +364,8 @@ __device__ __forceinline__ float load_eps(const void* p, long long i, int is_f32
 }
 
 __global__ void ddim_step_kernel(DdimStepParams p) {
+    griddep_wait();
+    griddep_launch_small();
     GRID_STRIDE(i, p.n) {
         const int ch = static_cast<int>((i / p.chan_stride) % p.C);
         const float c = load_eps(p.eps_c, i, p.eps_is_f32);
@@ -358,6 +393,8 @@ struct LincombArgs {
     int n_src;
 };
 __global__ void lincomb_kernel(float* out, LincombArgs a, long long n) {
+    griddep_wait();
+    griddep_launch_small();
     GRID_STRIDE(i, n) {
         float acc = 0.f;
         for (int s = 0; s < a.n_src; ++s) acc = fmaf(a.coef[s], a.src[s][i], acc);
@@ -367,6 +404,8 @@ __global__ void lincomb_kernel(float* out, LincombArgs a, long long n) {
 
 __global__ void cfg_x0_kernel(const float* x, const void* ec, const void* eu, int eps_f32, float* x0, long long n, float g,
                               float alpha, float sigma, int fp16) {
+    griddep_wait();
+    griddep_launch_small();
     GRID_STRIDE(i, n) {
         float e = load_eps(ec, i, eps_f32);
         if (eu != nullptr) e = cfg_combine(e, load_eps(eu, i, eps_f32), g, fp16);
@@ -381,26 +420,26 @@ inline int ok() { return cudaGetLastError() == cudaSuccess ? 0 : -2; }
 int ingest_latent(const void* x, int x_is_f32, __half* tok, long long ld, int cpad, int B, int C, int F, int h, int w,
                   float scale, cudaStream_t stream) {
     const long long n = static_cast<long long>(B) * F * h * w * cpad;
-    ingest_kernel<<<grid_for(n, 256), 256, 0, stream>>>(x, x_is_f32, tok, ld, cpad, B, C, F, h, w, scale);
+    launch_pdl(ingest_kernel, grid_for(n, 256), 256, 0, stream, x, x_is_f32, tok, ld, cpad, B, C, F, h, w, scale);
     return ok();
 }
 int egress_latent(const __half* tok, long long ld, void* out, int out_is_f32, int B, int C, int F, int h, int w,
                   cudaStream_t stream) {
     const long long n = static_cast<long long>(B) * C * F * h * w;
-    egress_kernel<<<grid_for(n, 256), 256, 0, stream>>>(tok, ld, out, out_is_f32, B, C, F, h, w);
+    launch_pdl(egress_kernel, grid_for(n, 256), 256, 0, stream, tok, ld, out, out_is_f32, B, C, F, h, w);
     return ok();
 }
 int upsample2x(const __half* x, __half* y, int nframes, int h, int w, int C, cudaStream_t stream) {
     if (C % 8) return -1;
     const long long n = static_cast<long long>(nframes) * 4 * h * w * (C / 8);
-    upsample2x_kernel<<<grid_for(n, 256), 256, 0, stream>>>(reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(y),
+    launch_pdl(upsample2x_kernel, grid_for(n, 256), 256, 0, stream, reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(y),
                                                             nframes, h, w, C / 8);
     return ok();
 }
 int im2col_s2(const __half* x, __half* col, int nframes, int h, int w, int C, cudaStream_t stream) {
     if (C % 8) return -1;
     const long long n = static_cast<long long>(nframes) * ((h + 1) / 2) * ((w + 1) / 2) * 9 * (C / 8);
-    im2col_s2_kernel<<<grid_for(n, 256), 256, 0, stream>>>(reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(col),
+    launch_pdl(im2col_s2_kernel, grid_for(n, 256), 256, 0, stream, reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(col),
                                                            nframes, h, w, C / 8);
     return ok();
 }
@@ -408,67 +447,67 @@ int concat_cols(const __half* a, long long lda, int Ca, const __half* b, long lo
                 long long ldo, long long rows, cudaStream_t stream) {
     if ((Ca % 8) || (Cb % 8) || (lda % 8) || (ldb % 8) || (ldo % 8)) return -1;
     const long long n = rows * ((Ca + Cb) / 8);
-    concat_kernel<<<grid_for(n, 256), 256, 0, stream>>>(a, lda, Ca / 8, b, ldb, Cb / 8, out, ldo, rows);
+    launch_pdl(concat_kernel, grid_for(n, 256), 256, 0, stream, a, lda, Ca / 8, b, ldb, Cb / 8, out, ldo, rows);
     return ok();
 }
 int time_sinusoid(const float* t, __half* out, int B, int dim, cudaStream_t stream) {
-    time_sinusoid_kernel<<<grid_for(static_cast<long long>(B) * dim, 256), 256, 0, stream>>>(t, out, B, dim);
+    launch_pdl(time_sinusoid_kernel, grid_for(static_cast<long long>(B) * dim, 256), 256, 0, stream, t, out, B, dim);
     return ok();
 }
 int small_linear(const __half* x, long long ldx, const __half* W, const __half* bias, const __half* addend, __half* y,
                  long long ldy, int B, int N, int K, int silu_in, cudaStream_t stream) {
     if ((K % 8) || (ldx % 8)) return -1;
-    small_linear_kernel<<<(N + 7) / 8, 256, 0, stream>>>(x, ldx, W, bias, addend, y, ldy, B, N, K, silu_in);
+    launch_pdl(small_linear_kernel, (N + 7) / 8, 256, 0, stream, x, ldx, W, bias, addend, y, ldy, B, N, K, silu_in);
     return ok();
 }
 int softmax_rows(const __half* x, __half* y, long long rows, int cols, float scale, cudaStream_t stream) {
-    softmax_rows_kernel<<<static_cast<unsigned int>((rows + 7) / 8), 256, 0, stream>>>(x, y, rows, cols, scale);
+    launch_pdl(softmax_rows_kernel, static_cast<unsigned int>((rows + 7) / 8), 256, 0, stream, x, y, rows, cols, scale);
     return ok();
 }
 int transpose_batched(const __half* x, __half* y, int nb, int R, int C, cudaStream_t stream) {
     dim3 grid((C + 31) / 32, (R + 31) / 32, nb);
-    transpose_kernel<<<grid, dim3(32, 8), 0, stream>>>(x, y, R, C);
+    launch_pdl(transpose_kernel, grid, dim3(32, 8), 0, stream, x, y, R, C);
     return ok();
 }
 int frames_to_u8(const __half* tok, long long ld, uint8_t* out, long long pixels, cudaStream_t stream) {
-    frames_to_u8_kernel<<<grid_for(pixels * 3, 256), 256, 0, stream>>>(tok, ld, out, pixels);
+    launch_pdl(frames_to_u8_kernel, grid_for(pixels * 3, 256), 256, 0, stream, tok, ld, out, pixels);
     return ok();
 }
 int frames_to_f32_nchw(const __half* tok, long long ld, float* out, int n, int H, int W, cudaStream_t stream) {
-    frames_to_f32_kernel<<<grid_for(static_cast<long long>(n) * 3 * H * W, 256), 256, 0, stream>>>(tok, ld, out, n, H, W);
+    launch_pdl(frames_to_f32_kernel, grid_for(static_cast<long long>(n) * 3 * H * W, 256), 256, 0, stream, tok, ld, out, n, H, W);
     return ok();
 }
 int pack_conv_weight(const void* src, int src_is_f32, __half* dst, int Cout, int Cin, int taps, int n_alloc, int k_alloc,
                      cudaStream_t stream) {
     const long long n = static_cast<long long>(taps) * n_alloc * k_alloc;
-    pack_conv_kernel<<<grid_for(n, 256), 256, 0, stream>>>(src, src_is_f32, dst, Cout, Cin, taps, n_alloc, k_alloc);
+    launch_pdl(pack_conv_kernel, grid_for(n, 256), 256, 0, stream, src, src_is_f32, dst, Cout, Cin, taps, n_alloc, k_alloc);
     return ok();
 }
 int pack_geglu_weight(const void* w, const void* b, int src_is_f32, __half* wdst, __half* bdst, int H, int K, int bn,
                       cudaStream_t stream) {
     if ((2 * H) % bn) return -1;
-    pack_geglu_kernel<<<grid_for(static_cast<long long>(2) * H * K, 256), 256, 0, stream>>>(w, b, src_is_f32, wdst, bdst, H, K, bn);
+    launch_pdl(pack_geglu_kernel, grid_for(static_cast<long long>(2) * H * K, 256), 256, 0, stream, w, b, src_is_f32, wdst, bdst, H, K, bn);
     return ok();
 }
 int splitk_reduce(const float* part, int splits, long long split_stride, long long rows, int N, const __half* bias,
                   int bias_rows, long long bias_stride, const __half* residual, long long ldr, __half* out, long long ldo,
                   cudaStream_t stream) {
     if ((N & 7) || (ldo & 7) || (residual && (ldr & 7)) || (bias && (bias_stride & 7))) return -1;
-    splitk_reduce_kernel<<<grid_for(rows * (N / 8), 256), 256, 0, stream>>>(part, splits, split_stride, rows, N / 8, bias,
+    launch_pdl(splitk_reduce_kernel, grid_for(rows * (N / 8), 256), 256, 0, stream, part, splits, split_stride, rows, N / 8, bias,
                                                                             bias_rows, bias_stride, residual, ldr, out, ldo);
     return ok();
 }
 int fold_ln_into_linear(const __half* w, const __half* bias, const __half* gamma, const __half* beta, __half* wout,
                         float* colsum, float* bias32, int N, int K, cudaStream_t stream) {
-    fold_ln_kernel<<<(N + 7) / 8, 256, 0, stream>>>(w, bias, gamma, beta, wout, colsum, bias32, N, K);
+    launch_pdl(fold_ln_kernel, (N + 7) / 8, 256, 0, stream, w, bias, gamma, beta, wout, colsum, bias32, N, K);
     return ok();
 }
 int convert_to_f16(const void* src, int src_is_f32, __half* dst, long long n, cudaStream_t stream) {
-    convert_kernel<<<grid_for(n, 256), 256, 0, stream>>>(src, src_is_f32, dst, n);
+    launch_pdl(convert_kernel, grid_for(n, 256), 256, 0, stream, src, src_is_f32, dst, n);
     return ok();
 }
 int ddim_step(const DdimStepParams& p, cudaStream_t stream) {
-    ddim_step_kernel<<<grid_for(p.n, 256), 256, 0, stream>>>(p);
+    launch_pdl(ddim_step_kernel, grid_for(p.n, 256), 256, 0, stream, p);
     return ok();
 }
 int lincomb(float* out, const float* const* src, const float* coef, int n_src, long long n, cudaStream_t stream) {
@@ -479,12 +518,12 @@ int lincomb(float* out, const float* const* src, const float* coef, int n_src, l
         a.coef[i] = coef[i];
     }
     a.n_src = n_src;
-    lincomb_kernel<<<grid_for(n, 256), 256, 0, stream>>>(out, a, n);
+    launch_pdl(lincomb_kernel, grid_for(n, 256), 256, 0, stream, out, a, n);
     return ok();
 }
 int cfg_x0(const float* x, const void* eps_c, const void* eps_u, int eps_is_f32, float* x0, long long n, float g,
            float alpha, float sigma, int cfg_fp16, cudaStream_t stream) {
-    cfg_x0_kernel<<<grid_for(n, 256), 256, 0, stream>>>(x, eps_c, eps_u, eps_is_f32, x0, n, g, alpha, sigma, cfg_fp16);
+    launch_pdl(cfg_x0_kernel, grid_for(n, 256), 256, 0, stream, x, eps_c, eps_u, eps_is_f32, x0, n, g, alpha, sigma, cfg_fp16);
     return ok();
 }
 

@@ -7,6 +7,7 @@
 //                               fp32 accumulator in TMEM; tcgen05.commit releases the smem stage / publishes the tile
 //   warps 2..9  epilogue      : tcgen05.ld 32 lanes x 32 columns -> registers -> alpha, bias, residual, GEGLU -> HBM
 // Roofline: tensor-bound (2*M*N*K*taps flop per launch) whenever K*taps is large; see DESIGN.md.
+#include "common.cuh"
 #include "gemm_tc.cuh"
 #include "ptx.cuh"
 
@@ -98,6 +99,7 @@ __global__ void __launch_bounds__(n_threads(GEGLU), 1) gemm_tc_kernel(const __gr
     else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    griddep_wait();        // everything above is independent of the previous kernel's output (PDL, common.cuh)
 
     // work items: (pair of consecutive M-tiles, N-tile); CTA `rank` of the pair owns M-tile 2*pm + rank
     const int pairs_m = (g.tiles_m + CG - 1) / CG;
@@ -169,6 +171,9 @@ __global__ void __launch_bounds__(n_threads(GEGLU), 1) gemm_tc_kernel(const __gr
                     }
                 }
             }
+            // nothing left to fetch: only this CTA's last MMAs / epilogue remain -> let the next kernel's CTAs be scheduled
+            // (they run their prologue and block in griddepcontrol.wait until this grid has completed)
+            griddep_launch();
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer (pair leader only)
@@ -746,15 +751,22 @@ int gemm_launch(const GemmPlan& plan, cudaStream_t stream) {
     cfg.blockDim = dim3(static_cast<unsigned>(n_threads((plan.desc.flags & GEMM_GEGLU) != 0)));
     cfg.dynamicSmemBytes = static_cast<size_t>(plan.smem);
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
+    unsigned na = 0;
     if (plan.cg == 2) {
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = 2;
-        attr[0].val.clusterDim.y = 1;
-        attr[0].val.clusterDim.z = 1;
-        cfg.attrs = attr;
-        cfg.numAttrs = 1;
+        attr[na].id = cudaLaunchAttributeClusterDimension;
+        attr[na].val.clusterDim.x = 2;
+        attr[na].val.clusterDim.y = 1;
+        attr[na].val.clusterDim.z = 1;
+        ++na;
     }
+    if (pdl_enabled()) {
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
+    cfg.attrs = attr;
+    cfg.numAttrs = na;
     void* args[1] = {const_cast<GemmDesc*>(&plan.desc)};
     return cudaLaunchKernelExC(&cfg, var->fn, args) == cudaSuccess ? 0 : -2;
 }

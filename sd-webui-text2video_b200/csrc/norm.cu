@@ -5,6 +5,7 @@
 // (F*h*w rows).  Both are "instances" of `rows_per_inst` consecutive rows here.
 // fp32 math throughout (the reference runs group_norm / layer_norm / SiLU-after-norm in fp32 under autocast and
 // rounds to fp16 only when the value enters the next conv/linear -- exactly where these kernels round).
+#include "common.cuh"
 #include "kernels.cuh"
 
 namespace t2v {
@@ -22,6 +23,8 @@ __global__ void __launch_bounds__(kStatsThreads) gn_stats_kernel(const __half* _
                                                                  float eps, float2* __restrict__ partial,
                                                                  unsigned int* __restrict__ counters,
                                                                  float2* __restrict__ stats) {
+    griddep_wait();
+    griddep_launch_small();
     extern __shared__ float sm[];          // [2*C] per-channel sum / sumsq
     float* s_sum = sm;
     float* s_sq = sm + C;
@@ -140,6 +143,8 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const __half* __restrict_
                                                        const float2* __restrict__ stats,
                                                        const __half* __restrict__ gamma,
                                                        const __half* __restrict__ beta, int silu) {
+    griddep_wait();
+    griddep_launch_small();
     extern __shared__ float ab[];          // a[C] | b[C]
     const int inst = blockIdx.y;
     const int C8 = C >> 3;
@@ -201,6 +206,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __half* __restrict
                                                         __half* __restrict__ y, long long ldy, long long rows, int C,
                                                         const __half* __restrict__ gamma,
                                                         const __half* __restrict__ beta, float eps) {
+    griddep_wait();
+    griddep_launch_small();
     const int lane = threadIdx.x & 31;
     const long long row = blockIdx.x * static_cast<long long>(blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= rows) return;
@@ -261,6 +268,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __half* __restrict
 
 __global__ void __launch_bounds__(256) ln_rowstats_kernel(const __half* __restrict__ x, long long ldx, long long rows, int C,
                                                           float eps, float2* __restrict__ out) {
+    griddep_wait();
+    griddep_launch_small();
     const int lane = threadIdx.x & 31;
     const long long row = blockIdx.x * static_cast<long long>(blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= rows) return;
@@ -337,7 +346,7 @@ int groupnorm_silu(const __half* x, long long ldx, __half* y, long long ldy, lon
     float2* stats = reinterpret_cast<float2*>(ws + kCounterBytes);
     float2* partial = stats + static_cast<size_t>(n_inst) * kGroups;
     if (phase != 2)
-        gn_stats_kernel<<<dim3(nchunks, n_inst), kStatsThreads, 2 * C * sizeof(float), stream>>>(
+        launch_pdl(gn_stats_kernel, dim3(nchunks, n_inst), kStatsThreads, 2 * C * sizeof(float), stream, 
             x, ldx, C, rows_per_inst, rpc, nchunks, eps, partial, counters, stats);
     if (phase == 1) return cudaGetLastError() == cudaSuccess ? 0 : -2;
     // rows per apply block: ~4 blocks per SM overall, at least 4 rows
@@ -347,14 +356,14 @@ int groupnorm_silu(const __half* x, long long ldx, __half* y, long long ldy, lon
     long long rpb = (rows_per_inst + per_inst - 1) / per_inst;
     if (rpb < 4) rpb = 4;
     const int nblk = static_cast<int>((rows_per_inst + rpb - 1) / rpb);
-    gn_apply_kernel<<<dim3(nblk, n_inst), 256, 2 * C * sizeof(float), stream>>>(x, ldx, y, ldy, C, rows_per_inst,
+    launch_pdl(gn_apply_kernel, dim3(nblk, n_inst), 256, 2 * C * sizeof(float), stream, x, ldx, y, ldy, C, rows_per_inst,
                                                                               static_cast<int>(rpb), stats, gamma, beta, silu);
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 
 int layernorm_rowstats(const __half* x, long long ldx, long long rows, int C, float eps, float2* out, cudaStream_t stream) {
     if (C % 8 != 0 || C > 2048) return -1;
-    ln_rowstats_kernel<<<static_cast<unsigned int>((rows + 7) / 8), 256, 0, stream>>>(x, ldx, rows, C, eps, out);
+    launch_pdl(ln_rowstats_kernel, static_cast<unsigned int>((rows + 7) / 8), 256, 0, stream, x, ldx, rows, C, eps, out);
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 
@@ -362,7 +371,7 @@ int layernorm(const __half* x, long long ldx, __half* y, long long ldy, long lon
               const __half* beta, float eps, cudaStream_t stream) {
     if (C % 8 != 0 || C > 2048) return -1;
     const long long blocks = (rows + 7) / 8;
-    layernorm_kernel<<<static_cast<unsigned int>(blocks), 256, 0, stream>>>(x, ldx, y, ldy, rows, C, gamma, beta, eps);
+    launch_pdl(layernorm_kernel, static_cast<unsigned int>(blocks), 256, 0, stream, x, ldx, y, ldy, rows, C, gamma, beta, eps);
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 
