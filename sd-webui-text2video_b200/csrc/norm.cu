@@ -5,6 +5,8 @@
 // (F*h*w rows).  Both are "instances" of `rows_per_inst` consecutive rows here.
 // fp32 math throughout (the reference runs group_norm / layer_norm / SiLU-after-norm in fp32 under autocast and
 // rounds to fp16 only when the value enters the next conv/linear -- exactly where these kernels round).
+#include <algorithm>
+
 #include "common.cuh"
 #include "kernels.cuh"
 
@@ -13,74 +15,105 @@ namespace t2v {
 namespace {
 
 constexpr int kGroups = 32;
-constexpr int kStatsThreads = 256;   // 32 vector lanes (x) x 8 row lanes (y)
+constexpr int kNormThreads = 320;    // = 8 x 40 = 4 x 80 = 2 x 160 vectors: whole rows of C = 320 / 640 / 1280 per pass
 constexpr size_t kCounterBytes = 1 << 20;   // up to 262144 norm instances (frames x samples) per call
+
+// Thread mapping shared by the statistics and the apply kernel: a block covers RL = 320 / (C/8) consecutive rows per
+// pass; thread (rl, vc) owns the 16-byte vector vc (8 channels) of rows rl, rl + RL, ...  Consecutive threads read
+// consecutive 16 B, the channel identity of a thread never changes (per-channel accumulators / scale+shift live in
+// registers), no integer division or shared-memory traffic in the streaming loop.
+struct RowMap {
+    int rl, vc, RL;
+    bool active;
+};
+__device__ __forceinline__ RowMap row_map(int C8) {
+    RowMap m;
+    m.RL = kNormThreads / C8;
+    m.rl = static_cast<int>(threadIdx.x) / C8;
+    m.vc = static_cast<int>(threadIdx.x) - m.rl * C8;
+    m.active = m.rl < m.RL;
+    return m;
+}
 
 // partial[(inst * nchunks + chunk) * 32 + g] = (sum, sumsq) ; the last block of an instance folds them (in
 // chunk order, double precision) into stats[inst*32+g] = (mean, rstd) -> deterministic, no float atomics in HBM.
-__global__ void __launch_bounds__(kStatsThreads) gn_stats_kernel(const __half* __restrict__ x, long long ld, int C,
-                                                                 int rows_per_inst, int rows_per_chunk, int nchunks,
-                                                                 float eps, float2* __restrict__ partial,
-                                                                 unsigned int* __restrict__ counters,
-                                                                 float2* __restrict__ stats) {
+__global__ void __launch_bounds__(kNormThreads) gn_stats_kernel(const __half* __restrict__ x, long long ld, int C,
+                                                                int rows_per_inst, int rows_per_chunk, int nchunks,
+                                                                float eps, float2* __restrict__ partial,
+                                                                unsigned int* __restrict__ counters,
+                                                                float2* __restrict__ stats) {
     griddep_wait();
     griddep_launch_small();
-    extern __shared__ float sm[];          // [2*C] per-channel sum / sumsq
-    float* s_sum = sm;
-    float* s_sq = sm + C;
+    extern __shared__ float sm[];          // red[2][RL][C] | s_sum[C] | s_sq[C]
     __shared__ bool is_last;
     const int inst = blockIdx.y;
     const int chunk = blockIdx.x;
-    const int tx = threadIdx.x & 31;
-    const int ty = threadIdx.x >> 5;
     const int C8 = C >> 3;
-    // cross-row-lane reduction through a fixed-order smem tree (no atomics: bit-reproducible run to run)
-    __shared__ float red[8][2][256];       // [row lane][sum|sumsq][32 vectors x 8 channels of the current pass]
+    const RowMap m = row_map(C8);
+    float* red = sm;                        // [2][RL][C]
+    float* s_sum = sm + 2 * m.RL * C;
+    float* s_sq = s_sum + C;
     const int r0 = chunk * rows_per_chunk;
     const int r1 = min(r0 + rows_per_chunk, rows_per_inst);
     const __half* base = x + static_cast<long long>(inst) * rows_per_inst * ld;
-    for (int v0 = 0; v0 < C8; v0 += 32) {          // uniform trip count: barriers inside are safe
-        const int vc = v0 + tx;
-        float s[8], q[8];
+    float s[8], q[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) s[e] = q[e] = 0.f;
-        if (vc < C8) {
-#pragma unroll 4
-            for (int r = r0 + ty; r < r1; r += 8) {
-                const uint4 v = __ldg(reinterpret_cast<const uint4*>(base + r * ld + vc * 8));
-                const __half2* h2 = reinterpret_cast<const __half2*>(&v);
+    for (int e = 0; e < 8; ++e) s[e] = q[e] = 0.f;
+    if (m.active) {
+        constexpr int U = 4;               // independent 16-byte loads in flight per thread
+        const __half* p = base + static_cast<long long>(r0 + m.rl) * ld + m.vc * 8;
+        const long long step = static_cast<long long>(m.RL) * ld;
+        int r = r0 + m.rl;
+        for (; r + (U - 1) * m.RL < r1; r += U * m.RL) {
+            uint4 v[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) v[u] = __ldg(reinterpret_cast<const uint4*>(p + u * step));
+            p += U * step;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const __half2* h2 = reinterpret_cast<const __half2*>(&v[u]);
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                     const float2 f = __half22float2(h2[e]);
                     s[2 * e] += f.x;
-                    q[2 * e] += f.x * f.x;
+                    q[2 * e] = fmaf(f.x, f.x, q[2 * e]);
                     s[2 * e + 1] += f.y;
-                    q[2 * e + 1] += f.y * f.y;
+                    q[2 * e + 1] = fmaf(f.y, f.y, q[2 * e + 1]);
                 }
             }
         }
+        for (; r < r1; r += m.RL) {
+            const uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
+            p += step;
+            const __half2* h2 = reinterpret_cast<const __half2*>(&v);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            red[ty][0][tx * 8 + e] = s[e];
-            red[ty][1][tx * 8 + e] = q[e];
-        }
-        __syncthreads();
-        {
-            const int ch = threadIdx.x;                 // 256 threads <-> 256 channels of this pass
-            const int gc = v0 * 8 + ch;
-            if (gc < C) {
-                float a = 0.f, b = 0.f;
-#pragma unroll
-                for (int y = 0; y < 8; ++y) {
-                    a += red[y][0][ch];
-                    b += red[y][1][ch];
-                }
-                s_sum[gc] = a;
-                s_sq[gc] = b;
+            for (int e = 0; e < 4; ++e) {
+                const float2 f = __half22float2(h2[e]);
+                s[2 * e] += f.x;
+                q[2 * e] = fmaf(f.x, f.x, q[2 * e]);
+                s[2 * e + 1] += f.y;
+                q[2 * e + 1] = fmaf(f.y, f.y, q[2 * e + 1]);
             }
         }
-        __syncthreads();
+        // cross-row-lane reduction through smem in a fixed order (no atomics: bit-reproducible run to run)
+        float4* d0 = reinterpret_cast<float4*>(red + (0 * m.RL + m.rl) * C + m.vc * 8);
+        float4* d1 = reinterpret_cast<float4*>(red + (1 * m.RL + m.rl) * C + m.vc * 8);
+        d0[0] = make_float4(s[0], s[1], s[2], s[3]);
+        d0[1] = make_float4(s[4], s[5], s[6], s[7]);
+        d1[0] = make_float4(q[0], q[1], q[2], q[3]);
+        d1[1] = make_float4(q[4], q[5], q[6], q[7]);
     }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += kNormThreads) {
+        float a = 0.f, b = 0.f;
+        for (int y = 0; y < m.RL; ++y) {
+            a += red[(0 * m.RL + y) * C + c];
+            b += red[(1 * m.RL + y) * C + c];
+        }
+        s_sum[c] = a;
+        s_sq[c] = b;
+    }
+    __syncthreads();
     const int cpg = C / kGroups;
     if (threadIdx.x < kGroups) {
         float a = 0.f, b = 0.f;
@@ -102,14 +135,14 @@ __global__ void __launch_bounds__(kStatsThreads) gn_stats_kernel(const __half* _
         // fold the chunk partials: 8 thread-parts per group read strided chunks (independent L2 loads in flight), then a
         // fixed-order combine -> deterministic and no serial chain of nchunks dependent loads
         __shared__ double fold[8][kGroups][2];
-        {
+        if (threadIdx.x < 256) {
             const int gidx = threadIdx.x & 31, part = threadIdx.x >> 5;
             double a = 0.0, b = 0.0;
 #pragma unroll 4
             for (int ch = part; ch < nchunks; ch += 8) {
-                const float2 p = __ldcg(&partial[(static_cast<long long>(inst) * nchunks + ch) * kGroups + gidx]);
-                a += p.x;
-                b += p.y;
+                const float2 pp = __ldcg(&partial[(static_cast<long long>(inst) * nchunks + ch) * kGroups + gidx]);
+                a += pp.x;
+                b += pp.y;
             }
             fold[part][gidx][0] = a;
             fold[part][gidx][1] = b;
@@ -133,71 +166,84 @@ __global__ void __launch_bounds__(kStatsThreads) gn_stats_kernel(const __half* _
     }
 }
 
-__device__ __forceinline__ float silu_f(float v) { return v / (1.0f + __expf(-v)); }
+// x * sigmoid(x) with one ex2 and one rcp on the MUFU (no IEEE division): the apply pass is MUFU-limited otherwise
+__device__ __forceinline__ float silu_f(float v) {
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(v * -1.4426950408889634f));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+    return v * r;
+}
 
-// grid = (row blocks, instances).  Each block first folds (mean, rstd, gamma, beta) of ITS instance into per-channel
-// scale/shift in smem, then streams its rows: y = act(x * a[c] + b[c]) -- one FMA per element, 16-byte accesses.
-__global__ void __launch_bounds__(256) gn_apply_kernel(const __half* __restrict__ x, long long ldx,
-                                                       __half* __restrict__ y, long long ldy, int C,
-                                                       int rows_per_inst, int rows_per_block,
-                                                       const float2* __restrict__ stats,
-                                                       const __half* __restrict__ gamma,
-                                                       const __half* __restrict__ beta, int silu) {
+template <bool SILU>
+__device__ __forceinline__ uint4 gn_apply_vec(const uint4& v, const float (&a)[8], const float (&b)[8]) {
+    const __half2* h2 = reinterpret_cast<const __half2*>(&v);
+    uint4 o;
+    __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const float2 f = __half22float2(h2[e]);
+        float u0 = fmaf(f.x, a[2 * e], b[2 * e]);
+        float u1 = fmaf(f.y, a[2 * e + 1], b[2 * e + 1]);
+        if (SILU) {
+            u0 = silu_f(u0);
+            u1 = silu_f(u1);
+        }
+        oh[e] = __floats2half2_rn(u0, u1);
+    }
+    return o;
+}
+
+// grid = (row blocks, instances).  Each thread folds (mean, rstd, gamma, beta) of ITS 8 channels into scale/shift
+// registers, then streams its rows: y = act(x * a[c] + b[c]) -- one FMA (+ SiLU) per element, 16-byte accesses.
+template <bool SILU>
+__global__ void __launch_bounds__(kNormThreads) gn_apply_kernel(const __half* __restrict__ x, long long ldx,
+                                                                __half* __restrict__ y, long long ldy, int C,
+                                                                int rows_per_inst, int rows_per_block,
+                                                                const float2* __restrict__ stats,
+                                                                const __half* __restrict__ gamma,
+                                                                const __half* __restrict__ beta) {
     griddep_wait();
     griddep_launch_small();
-    extern __shared__ float ab[];          // a[C] | b[C]
     const int inst = blockIdx.y;
     const int C8 = C >> 3;
     const int cpg = C / kGroups;
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        const float2 ms = __ldg(stats + inst * kGroups + c / cpg);
-        const float a = ms.y * __half2float(__ldg(gamma + c));
-        ab[c] = a;
-        ab[C + c] = __half2float(__ldg(beta + c)) - ms.x * a;
+    const RowMap m = row_map(C8);
+    if (!m.active) return;
+    float a[8], b[8];
+    {
+        const uint4 gv = __ldg(reinterpret_cast<const uint4*>(gamma + m.vc * 8));
+        const uint4 bv = __ldg(reinterpret_cast<const uint4*>(beta + m.vc * 8));
+        const __half* gh = reinterpret_cast<const __half*>(&gv);
+        const __half* bh = reinterpret_cast<const __half*>(&bv);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const float2 ms = __ldg(stats + inst * kGroups + (m.vc * 8 + e) / cpg);
+            a[e] = ms.y * __half2float(gh[e]);
+            b[e] = __half2float(bh[e]) - ms.x * a[e];
+        }
     }
-    __syncthreads();
     const int r0 = blockIdx.x * rows_per_block;
     const int r1 = min(r0 + rows_per_block, rows_per_inst);
-    const long long base_row = static_cast<long long>(inst) * rows_per_inst;
-    const int total = (r1 - r0) * C8;
+    const long long row0 = static_cast<long long>(inst) * rows_per_inst + r0 + m.rl;
+    const __half* px = x + row0 * ldx + m.vc * 8;
+    __half* py = y + row0 * ldy + m.vc * 8;
+    const long long sx = static_cast<long long>(m.RL) * ldx, sy = static_cast<long long>(m.RL) * ldy;
     constexpr int U = 4;                   // independent 16-byte loads in flight per thread
-    for (int i0 = threadIdx.x; i0 < total; i0 += blockDim.x * U) {
+    int r = r0 + m.rl;
+    for (; r + (U - 1) * m.RL < r1; r += U * m.RL) {
         uint4 v[U];
-        int rr[U], vv[U];
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int i = i0 + u * blockDim.x;
-            rr[u] = i / C8;
-            vv[u] = i - rr[u] * C8;
-            if (i < total) v[u] = __ldg(reinterpret_cast<const uint4*>(x + (base_row + r0 + rr[u]) * ldx + vv[u] * 8));
-        }
+        for (int u = 0; u < U; ++u) v[u] = __ldg(reinterpret_cast<const uint4*>(px + u * sx));
+        px += U * sx;
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int i = i0 + u * blockDim.x;
-            if (i >= total) continue;
-            const int vc = vv[u];
-            const __half* xh = reinterpret_cast<const __half*>(&v[u]);
-            const float4 a0 = *reinterpret_cast<const float4*>(ab + vc * 8);
-            const float4 a1 = *reinterpret_cast<const float4*>(ab + vc * 8 + 4);
-            const float4 b0 = *reinterpret_cast<const float4*>(ab + C + vc * 8);
-            const float4 b1 = *reinterpret_cast<const float4*>(ab + C + vc * 8 + 4);
-            float f[8] = {fmaf(__half2float(xh[0]), a0.x, b0.x), fmaf(__half2float(xh[1]), a0.y, b0.y),
-                          fmaf(__half2float(xh[2]), a0.z, b0.z), fmaf(__half2float(xh[3]), a0.w, b0.w),
-                          fmaf(__half2float(xh[4]), a1.x, b1.x), fmaf(__half2float(xh[5]), a1.y, b1.y),
-                          fmaf(__half2float(xh[6]), a1.z, b1.z), fmaf(__half2float(xh[7]), a1.w, b1.w)};
-            uint4 o;
-            __half2* oh = reinterpret_cast<__half2*>(&o);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                float u0 = f[2 * e], u1 = f[2 * e + 1];
-                if (silu) {
-                    u0 = silu_f(u0);
-                    u1 = silu_f(u1);
-                }
-                oh[e] = __floats2half2_rn(u0, u1);
-            }
-            *reinterpret_cast<uint4*>(y + (base_row + r0 + rr[u]) * ldy + vc * 8) = o;
-        }
+        for (int u = 0; u < U; ++u) *reinterpret_cast<uint4*>(py + u * sy) = gn_apply_vec<SILU>(v[u], a, b);
+        py += U * sy;
+    }
+    for (; r < r1; r += m.RL) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(px));
+        px += sx;
+        *reinterpret_cast<uint4*>(py) = gn_apply_vec<SILU>(v, a, b);
+        py += sy;
     }
 }
 
@@ -266,52 +312,84 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __half* __restrict
     }
 }
 
+// (mean, rstd) per row; one warp per row, two rows in flight per warp, grid-stride over rows (a few resident blocks
+// per SM instead of one short-lived block per 8 rows).  NV = ceil(C / 256) 16-byte vectors per lane.
+template <int NV>
 __global__ void __launch_bounds__(256) ln_rowstats_kernel(const __half* __restrict__ x, long long ldx, long long rows, int C,
                                                           float eps, float2* __restrict__ out) {
     griddep_wait();
     griddep_launch_small();
     const int lane = threadIdx.x & 31;
-    const long long row = blockIdx.x * static_cast<long long>(blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (row >= rows) return;
     const int C8 = C >> 3;
-    constexpr int MAXV = 8;
-    uint4 v[MAXV];
-    float s = 0.f;
+    const float inv_c = 1.0f / static_cast<float>(C);
+    const long long wstride = static_cast<long long>(gridDim.x) * (blockDim.x >> 5);
+    long long row = blockIdx.x * static_cast<long long>(blockDim.x >> 5) + (threadIdx.x >> 5);
+    for (; row < rows; row += 2 * wstride) {
+        const long long rowb = row + wstride;
+        const bool hb = rowb < rows;
+        uint4 va[NV], vb[NV];
 #pragma unroll
-    for (int k = 0; k < MAXV; ++k) {
-        const int vc = lane + k * 32;
-        if (vc < C8) {
-            v[k] = __ldg(reinterpret_cast<const uint4*>(x + row * ldx + vc * 8));
-            const __half2* h2 = reinterpret_cast<const __half2*>(&v[k]);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const float2 f = __half22float2(h2[e]);
-                s += f.x + f.y;
+        for (int k = 0; k < NV; ++k) {
+            const int vc = lane + k * 32;
+            va[k] = make_uint4(0u, 0u, 0u, 0u);
+            vb[k] = make_uint4(0u, 0u, 0u, 0u);
+            if (vc < C8) {
+                va[k] = __ldg(reinterpret_cast<const uint4*>(x + row * ldx + vc * 8));
+                if (hb) vb[k] = __ldg(reinterpret_cast<const uint4*>(x + rowb * ldx + vc * 8));
             }
         }
-    }
+        float sa = 0.f, sb = 0.f;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    const float mean = s / C;
-    float q = 0.f;
-#pragma unroll
-    for (int k = 0; k < MAXV; ++k) {
-        const int vc = lane + k * 32;
-        if (vc < C8) {
-            const __half2* h2 = reinterpret_cast<const __half2*>(&v[k]);
+        for (int k = 0; k < NV; ++k) {
+            const __half2* ha = reinterpret_cast<const __half2*>(&va[k]);
+            const __half2* hbp = reinterpret_cast<const __half2*>(&vb[k]);
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                const float2 f = __half22float2(h2[e]);
-                q += (f.x - mean) * (f.x - mean) + (f.y - mean) * (f.y - mean);
+                const float2 fa = __half22float2(ha[e]);
+                const float2 fb = __half22float2(hbp[e]);
+                sa += fa.x + fa.y;
+                sb += fb.x + fb.y;
             }
         }
-    }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-    if (lane == 0) out[row] = make_float2(mean, rsqrtf(q / C + eps));
+        for (int o = 16; o > 0; o >>= 1) {
+            sa += __shfl_xor_sync(0xffffffffu, sa, o);
+            sb += __shfl_xor_sync(0xffffffffu, sb, o);
+        }
+        const float ma = sa * inv_c, mb = sb * inv_c;
+        float qa = 0.f, qb = 0.f;
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            if (lane + k * 32 < C8) {          // padding vectors are zero, not (0 - mean)
+                const __half2* ha = reinterpret_cast<const __half2*>(&va[k]);
+                const __half2* hbp = reinterpret_cast<const __half2*>(&vb[k]);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float2 fa = __half22float2(ha[e]);
+                    const float2 fb = __half22float2(hbp[e]);
+                    qa += (fa.x - ma) * (fa.x - ma) + (fa.y - ma) * (fa.y - ma);
+                    qb += (fb.x - mb) * (fb.x - mb) + (fb.y - mb) * (fb.y - mb);
+                }
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            qa += __shfl_xor_sync(0xffffffffu, qa, o);
+            qb += __shfl_xor_sync(0xffffffffu, qb, o);
+        }
+        if (lane == 0) {
+            out[row] = make_float2(ma, rsqrtf(qa * inv_c + eps));
+            if (hb) out[rowb] = make_float2(mb, rsqrtf(qb * inv_c + eps));
+        }
+    }
 }
 
 }  // namespace
+
+static size_t stats_smem_bytes(int C) {
+    const int RL = kNormThreads / (C / 8);
+    return static_cast<size_t>(2 * RL * C + 2 * C) * sizeof(float);
+}
 
 int gn_rows_per_chunk(int rows_per_inst, int n_inst, int num_sms) {
     // ~2 blocks per SM: fat blocks amortise the per-block latency chain (few dependent loads per thread otherwise)
@@ -336,7 +414,7 @@ size_t gn_workspace_bytes(int rows_per_inst, int n_inst, int num_sms) {
 int groupnorm_silu(const __half* x, long long ldx, __half* y, long long ldy, long long rows, int C, int rows_per_inst,
                    const __half* gamma, const __half* beta, float eps, int silu, void* workspace, int num_sms,
                    cudaStream_t stream, int phase) {
-    if (C % 32 != 0 || C % 8 != 0 || rows % rows_per_inst != 0) return -1;
+    if (C % 32 != 0 || C % 8 != 0 || C / 8 > kNormThreads || rows % rows_per_inst != 0 || (ldx & 7) != 0 || (ldy & 7) != 0) return -1;
     const int n_inst = static_cast<int>(rows / rows_per_inst);
     const int rpc = gn_rows_per_chunk(rows_per_inst, n_inst, num_sms);
     const int nchunks = (rows_per_inst + rpc - 1) / rpc;
@@ -346,8 +424,8 @@ int groupnorm_silu(const __half* x, long long ldx, __half* y, long long ldy, lon
     float2* stats = reinterpret_cast<float2*>(ws + kCounterBytes);
     float2* partial = stats + static_cast<size_t>(n_inst) * kGroups;
     if (phase != 2)
-        launch_pdl(gn_stats_kernel, dim3(nchunks, n_inst), kStatsThreads, 2 * C * sizeof(float), stream, 
-            x, ldx, C, rows_per_inst, rpc, nchunks, eps, partial, counters, stats);
+        launch_pdl(gn_stats_kernel, dim3(nchunks, n_inst), kNormThreads, stats_smem_bytes(C), stream, x, ldx, C, rows_per_inst,
+                   rpc, nchunks, eps, partial, counters, stats);
     if (phase == 1) return cudaGetLastError() == cudaSuccess ? 0 : -2;
     // rows per apply block: ~4 blocks per SM overall, at least 4 rows
     long long want_blocks = static_cast<long long>(num_sms) * 4;
@@ -356,14 +434,24 @@ int groupnorm_silu(const __half* x, long long ldx, __half* y, long long ldy, lon
     long long rpb = (rows_per_inst + per_inst - 1) / per_inst;
     if (rpb < 4) rpb = 4;
     const int nblk = static_cast<int>((rows_per_inst + rpb - 1) / rpb);
-    launch_pdl(gn_apply_kernel, dim3(nblk, n_inst), 256, 2 * C * sizeof(float), stream, x, ldx, y, ldy, C, rows_per_inst,
-                                                                              static_cast<int>(rpb), stats, gamma, beta, silu);
+    if (silu)
+        launch_pdl(gn_apply_kernel<true>, dim3(nblk, n_inst), kNormThreads, 0, stream, x, ldx, y, ldy, C, rows_per_inst,
+                   static_cast<int>(rpb), stats, gamma, beta);
+    else
+        launch_pdl(gn_apply_kernel<false>, dim3(nblk, n_inst), kNormThreads, 0, stream, x, ldx, y, ldy, C, rows_per_inst,
+                   static_cast<int>(rpb), stats, gamma, beta);
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 
 int layernorm_rowstats(const __half* x, long long ldx, long long rows, int C, float eps, float2* out, cudaStream_t stream) {
     if (C % 8 != 0 || C > 2048) return -1;
-    launch_pdl(ln_rowstats_kernel, static_cast<unsigned int>((rows + 7) / 8), 256, 0, stream, x, ldx, rows, C, eps, out);
+    const long long need = (rows + 15) / 16;                           // 8 warps x 2 rows per block pass
+    const unsigned int grid = static_cast<unsigned int>(std::min<long long>(need, static_cast<long long>(num_sms()) * 8));
+    const int nv = (C / 8 + 31) / 32;
+    if (nv <= 2) launch_pdl(ln_rowstats_kernel<2>, grid, 256, 0, stream, x, ldx, rows, C, eps, out);
+    else if (nv <= 3) launch_pdl(ln_rowstats_kernel<3>, grid, 256, 0, stream, x, ldx, rows, C, eps, out);
+    else if (nv <= 5) launch_pdl(ln_rowstats_kernel<5>, grid, 256, 0, stream, x, ldx, rows, C, eps, out);
+    else launch_pdl(ln_rowstats_kernel<8>, grid, 256, 0, stream, x, ldx, rows, C, eps, out);
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 
