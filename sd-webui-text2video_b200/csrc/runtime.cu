@@ -208,6 +208,7 @@ int Builder::gemm(GemmProblem& p) {
         const long long tiles = tiles_m * ((p.N + 255) / 256);
         const int kt = p.ntaps * ((p.K + GEMM_BLOCK_K - 1) / GEMM_BLOCK_K);
         int S = static_cast<int>(std::min<long long>(std::min<long long>(sms_ / std::max<long long>(tiles, 1), kt / 4), 8));
+        // (64-wide tiles without split-K were measured equal within 0.3 % on the whole forward: same MMA time per CTA)
         if (tiles * 2 <= sms_ && S >= 2) {
             const long long nrows = static_cast<long long>(rows);
             float* scratch = reinterpret_cast<float*>(arena_->alloc(static_cast<size_t>(S) * nrows * p.N * sizeof(float)));
