@@ -21,6 +21,7 @@ from oracle import ref_shim                                   # noqa: E402
 from oracle import unet_oracle as UO                          # noqa: E402
 from oracle import vae_oracle as VO                           # noqa: E402
 from oracle import samplers_oracle as SO                      # noqa: E402
+from oracle import vc_oracle as VC                            # noqa: E402
 
 GOLD = os.path.join(ROOT, 'tests', 'golden')
 
@@ -266,6 +267,75 @@ def gold_vae(m):
                os.path.join(GOLD, 'vae_decode.pt'))
 
 
+
+def build_ref_vc_unet(cfg: VC.VCConfig):
+    from videocrafter.lvdm.models.modules.openaimodel3d import UNetModel
+    return UNetModel(image_size=32, in_channels=cfg.in_channels, out_channels=cfg.out_channels,
+                     model_channels=cfg.model_channels, attention_resolutions=list(cfg.attention_resolutions),
+                     num_res_blocks=cfg.num_res_blocks, channel_mult=list(cfg.channel_mult), num_heads=cfg.num_heads,
+                     transformer_depth=1, context_dim=cfg.context_dim, use_checkpoint=False, legacy=False, kernel_size_t=1,
+                     padding_t=0, temporal_length=cfg.temporal_length,
+                     use_relative_position=cfg.use_relative_position).eval()
+
+
+def gold_vc_unet(name, cfg: VC.VCConfig, B, T, h, w, L, wseed):
+    """VideoCrafter UNetModel: reference output on seeded inputs / weights; asserts the restatement."""
+    torch.manual_seed(0)
+    net = build_ref_vc_unet(cfg)
+    specs = VC.vc_param_specs(cfg)
+    sd = net.state_dict()
+    assert set(sd) == set(specs), (set(sd) ^ set(specs))
+    for k in sd:
+        assert tuple(sd[k].shape) == specs[k], k
+    W = UO.make_weights(specs, seed=wseed)
+    net.load_state_dict(W, strict=True)
+    g = torch.Generator('cpu').manual_seed(123)
+    x = torch.randn((B, 4, T, h, w), generator=g)
+    ctx = torch.randn((B, L, cfg.context_dim), generator=torch.Generator('cpu').manual_seed(2))
+    t = torch.tensor([981, 37][:B])
+    t0 = time.time()
+    with torch.no_grad():
+        ref = net(x, t, context=ctx)
+    t1 = time.time()
+    o = VC.vc_unet_forward(W, cfg, x, t, ctx)
+    err = (o - ref).abs().max().item()
+    print(f'[vc_unet:{name}] reference {t1 - t0:.1f}s; oracle-vs-reference max|d| = {err:.3e} '
+          f'(ref absmax {ref.abs().max().item():.3f}), params {sum(v.numel() for v in W.values()) / 1e6:.2f} M')
+    assert err <= 1e-5 * max(1.0, ref.abs().max().item())
+    torch.save({'wseed': wseed, 'x_seed': 123, 'ctx_seed': 2, 'shape': (B, 4, T, h, w), 'L': L, 't': t, 'out': ref,
+                'cfg': {'model_channels': cfg.model_channels, 'context_dim': cfg.context_dim,
+                        'temporal_length': cfg.temporal_length}},
+               os.path.join(GOLD, name + '.pt'))
+
+
+def gold_vc_ddim():
+    """lvdm/samplers/ddim.py DDIMSampler on the analytic eps-model (5-D latents, B = 2, with and without eta)."""
+    ref_shim.install()
+    from videocrafter.lvdm.samplers.ddim import DDIMSampler
+    DDIMSampler.register_buffer = lambda self, name, attr: setattr(self, name, attr)    # ddim.py:22-26 hard-codes "cuda"
+    betas = SO.linear_sd_betas()
+
+    class _LDM(_SchedModel):
+        def apply_model(self, x, t, c, **kw):
+            return analytic_model(x, t, c)
+    model = _LDM(betas)
+    g = torch.Generator('cpu').manual_seed(123)
+    x = torch.randn((2, 4, 5, 6, 7), generator=g)
+    c = torch.full((2, 77, 8), 0.25)
+    uc = torch.full((2, 77, 8), -0.5)
+    out = {'x_seed': 123, 'shape': tuple(x.shape), 'c_val': 0.25, 'uc_val': -0.5}
+    for S, scale, eta in ((50, 15.0, 0.0), (20, 7.5, 0.0), (10, 3.0, 0.5)):
+        smp = DDIMSampler(model)
+        smp.noise_gen.manual_seed(11)
+        r, _ = smp.sample(S=S, batch_size=2, shape=tuple(x.shape[1:]), conditioning=c, x_T=x, verbose=False,
+                          unconditional_guidance_scale=scale, unconditional_conditioning=uc, eta=eta)
+        o = VC.vc_ddim_sample(model, betas, x, S, c, uc, scale, eta=eta, noise_gen=torch.Generator('cpu').manual_seed(11))
+        print(f'[vc_ddim] S={S} g={scale} eta={eta}: oracle-vs-reference max|d| = {(r - o).abs().max().item():.3e}')
+        assert torch.allclose(r, o, rtol=0, atol=1e-6)
+        out[f'S{S}_g{scale}_eta{eta}'] = r
+    torch.save(out, os.path.join(GOLD, 'vc_ddim.pt'))
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     m = ref_shim.load_modelscope()
@@ -278,6 +348,10 @@ def main():
     gold_unet(m, 'unet_tiny', tiny, F=3, h=16, w=8, wseed=1, keep_taps=keep)
     if os.environ.get('T2V_GOLD_FULL', '1') == '1':
         gold_unet(m, 'unet_cfg1', UO.UNetConfig(), F=4, h=16, w=16, wseed=0, keep_taps=[])
+    gold_vc_ddim()
+    gold_vc_unet('vc_unet_tiny', VC.VCConfig(model_channels=64, context_dim=48, temporal_length=4), B=2, T=4, h=8, w=8, L=7, wseed=3)
+    if os.environ.get('T2V_GOLD_FULL', '1') == '1':
+        gold_vc_unet('vc_unet_full', VC.VCConfig(), B=1, T=16, h=16, w=16, L=77, wseed=0)
 
 
 if __name__ == '__main__':

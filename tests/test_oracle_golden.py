@@ -96,3 +96,41 @@ def test_oracle_unet_live_against_reference():
     with torch.no_grad():
         ref = net(x, t, y)
     assert torch.allclose(UO.unet_forward(W, cfg, x, t, y), ref, rtol=0, atol=3e-5)
+
+
+# ---------------------------------------------------------------------------------------- VideoCrafter
+from oracle import vc_oracle as VC  # noqa: E402
+
+
+def _vc_inputs(g):
+    B, _, T, h, w = g['shape']
+    x = torch.randn(g['shape'], generator=torch.Generator('cpu').manual_seed(g['x_seed']))
+    ctx = torch.randn((B, g['L'], g['cfg']['context_dim']), generator=torch.Generator('cpu').manual_seed(g['ctx_seed']))
+    return x, ctx
+
+
+@pytest.mark.parametrize('name', ['vc_unet_tiny', 'vc_unet_full'])
+def test_vc_unet_matches_reference_fixture(gold_dir, name):
+    g = torch.load(os.path.join(gold_dir, name + '.pt'))
+    cfg = VC.VCConfig(**g['cfg'])
+    W = UO.make_weights(VC.vc_param_specs(cfg), seed=g['wseed'])
+    x, ctx = _vc_inputs(g)
+    out = VC.vc_unet_forward(W, cfg, x, g['t'], ctx)
+    assert torch.allclose(out, g['out'], rtol=0, atol=2e-5)
+
+
+def test_vc_param_specs_count_public_config():
+    specs = VC.vc_param_specs(VC.VCConfig())
+    n = sum(int(torch.tensor(s).prod()) for s in specs.values())
+    assert len(specs) == 974 and abs(n / 1e6 - 958.9) < 0.1      # 958.9 M parameters
+
+
+@pytest.mark.parametrize('S,scale,eta', [(50, 15.0, 0.0), (20, 7.5, 0.0), (10, 3.0, 0.5)])
+def test_vc_ddim_matches_reference_fixture(gold_dir, S, scale, eta):
+    g = torch.load(os.path.join(gold_dir, 'vc_ddim.pt'))
+    x = torch.randn(g['shape'], generator=torch.Generator('cpu').manual_seed(g['x_seed']))
+    c = torch.full((2, 77, 8), g['c_val'])
+    uc = torch.full((2, 77, 8), g['uc_val'])
+    o = VC.vc_ddim_sample(lambda xx, t, cc: analytic_model(xx, t, cc), SO.linear_sd_betas(), x, S, c, uc, scale, eta=eta,
+                          noise_gen=torch.Generator('cpu').manual_seed(11))
+    assert torch.allclose(o, g[f'S{S}_g{scale}_eta{eta}'], rtol=0, atol=1e-6)
