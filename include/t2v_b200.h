@@ -135,6 +135,18 @@ int t2v_op_layernorm(const void* x, long long ldx, void* y, long long ldy, long 
 int t2v_op_attention(const void* q, const void* k, const void* v, void* o, long long q_bs, long long q_ss,
                      long long k_bs, long long k_ss, long long v_bs, long long v_ss, long long o_bs, long long o_ss,
                      int batch, int heads, int sq, int skv, int kv_batch_div, float scale, void* stream);
+/* same for head_dim in {8,16,32,40,80,160} (64 dispatches to t2v_op_attention's kernels): CrossAttention.forward of the
+ * VideoCrafter denoiser, videocrafter/lvdm/models/modules/attention_temporal.py:167-190 (8 heads of width C/8). */
+int t2v_op_attention_hd(const void* q, const void* k, const void* v, void* o, long long q_bs, long long q_ss,
+                        long long k_bs, long long k_ss, long long v_bs, long long v_ss, long long o_bs, long long o_ss,
+                        int batch, int heads, int head_dim, int sq, int skv, int kv_batch_div, float scale, void* stream);
+/* TemporalCrossAttention.forward with RelativePosition tables (attention_temporal.py:46-65, :107-144), context = x:
+ * sequences of T <= 16 frames; sequence s of n_seq lives at (s / seq_inner) * bs_outer + (s % seq_inner) * bs_inner, its
+ * frames `ss` elements apart; head h at column h * head_dim; tables [2*max_rel+1, head_dim] fp16, T - 1 <= max_rel. */
+int t2v_op_attention_relpos(const void* q, const void* k, const void* v, void* o, const void* table_k, const void* table_v,
+                            long long n_seq, long long seq_inner, long long bs_outer, long long bs_inner, long long ss,
+                            long long o_bs_outer, long long o_bs_inner, long long o_ss, int heads, int head_dim, int T,
+                            int max_rel, float scale, void* stream);
 int t2v_op_upsample2x(const void* x, void* y, int nframes, int h, int w, int C, void* stream);
 int t2v_op_im2col_s2(const void* x, void* col, int nframes, int h, int w, int C, void* stream);
 int t2v_op_time_sinusoid(const float* t, void* out, int B, int dim, void* stream);

@@ -153,6 +153,37 @@ int t2v_op_attention(const void* q, const void* k, const void* v, void* o, long 
     p.scale = scale; p.b_inner = 1; p.q_bsi = p.k_bsi = p.v_bsi = p.o_bsi = 0;
     return attention(p, reinterpret_cast<cudaStream_t>(stream));
 }
+int t2v_op_attention_hd(const void* q, const void* k, const void* v, void* o, long long q_bs, long long q_ss,
+                        long long k_bs, long long k_ss, long long v_bs, long long v_ss, long long o_bs, long long o_ss,
+                        int batch, int heads, int head_dim, int sq, int skv, int kv_batch_div, float scale, void* stream) {
+    AttnParams p;
+    memset(&p, 0, sizeof(p));
+    p.q = reinterpret_cast<const __half*>(q);
+    p.k = reinterpret_cast<const __half*>(k);
+    p.v = reinterpret_cast<const __half*>(v);
+    p.o = reinterpret_cast<__half*>(o);
+    p.q_bs = q_bs; p.q_ss = q_ss; p.k_bs = k_bs; p.k_ss = k_ss; p.v_bs = v_bs; p.v_ss = v_ss; p.o_bs = o_bs; p.o_ss = o_ss;
+    p.batch = batch; p.heads = heads; p.sq = sq; p.skv = skv; p.head_dim = head_dim; p.kv_batch_div = kv_batch_div;
+    p.scale = scale; p.b_inner = 1;
+    return head_dim == 64 ? attention(p, reinterpret_cast<cudaStream_t>(stream)) : attention_hd(p, reinterpret_cast<cudaStream_t>(stream));
+}
+int t2v_op_attention_relpos(const void* q, const void* k, const void* v, void* o, const void* table_k, const void* table_v,
+                            long long n_seq, long long seq_inner, long long bs_outer, long long bs_inner, long long ss,
+                            long long o_bs_outer, long long o_bs_inner, long long o_ss, int heads, int head_dim, int T,
+                            int max_rel, float scale, void* stream) {
+    RelposParams p;
+    memset(&p, 0, sizeof(p));
+    p.q = reinterpret_cast<const __half*>(q);
+    p.k = reinterpret_cast<const __half*>(k);
+    p.v = reinterpret_cast<const __half*>(v);
+    p.o = reinterpret_cast<__half*>(o);
+    p.table_k = reinterpret_cast<const __half*>(table_k);
+    p.table_v = reinterpret_cast<const __half*>(table_v);
+    p.n_seq = n_seq; p.seq_inner = seq_inner; p.bs_outer = bs_outer; p.bs_inner = bs_inner; p.ss = ss;
+    p.o_bs_outer = o_bs_outer; p.o_bs_inner = o_bs_inner; p.o_ss = o_ss;
+    p.heads = heads; p.head_dim = head_dim; p.T = T; p.max_rel = max_rel; p.scale = scale;
+    return attention_relpos(p, reinterpret_cast<cudaStream_t>(stream));
+}
 int t2v_op_upsample2x(const void* x, void* y, int nframes, int h, int w, int C, void* stream) {
     return upsample2x(reinterpret_cast<const __half*>(x), reinterpret_cast<__half*>(y), nframes, h, w, C,
                       reinterpret_cast<cudaStream_t>(stream));

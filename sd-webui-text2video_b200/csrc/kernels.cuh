@@ -37,6 +37,25 @@ struct AttnParams {
 };
 int attention(const AttnParams& p, cudaStream_t stream);
 
+// attention_hd.cu: head dims other than 64 (VideoCrafter: C/8 = 40 / 80 / 160) and temporal attention with
+// relative-position tables.  attention_hd takes the same AttnParams (head h at column h*head_dim).
+int attention_hd(const AttnParams& p, cudaStream_t stream);
+struct RelposParams {
+    const __half* q;
+    const __half* k;
+    const __half* v;
+    __half* o;
+    const __half* table_k;    // [2*max_rel+1, head_dim] relative_position_k.embeddings_table
+    const __half* table_v;    // [2*max_rel+1, head_dim]
+    long long n_seq;          // sequences (= samples * pixels); sequence s -> (s / seq_inner, s % seq_inner)
+    long long seq_inner;
+    long long bs_outer, bs_inner, ss;          // q/k/v: outer / inner sequence strides and the frame stride (elements)
+    long long o_bs_outer, o_bs_inner, o_ss;
+    int heads, head_dim, T, max_rel;
+    float scale;
+};
+int attention_relpos(const RelposParams& p, cudaStream_t stream);
+
 // attention_tc.cu: tcgen05 / TMEM / TMA kernel for long self-attention sequences (sq >= 256, skv >= 128, one-level batch).
 // The plan holds the three tensor maps (encoded once per UNet plan, the launch itself is host-side free of driver calls).
 struct AttnTcPlan {

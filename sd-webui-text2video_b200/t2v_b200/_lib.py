@@ -48,6 +48,10 @@ SIGNATURES = {
     't2v_op_layernorm': (c_int, [P, c_ll, P, c_ll, c_ll, c_int, P, P, c_float, P]),
     't2v_op_attention': (c_int, [P, P, P, P, c_ll, c_ll, c_ll, c_ll, c_ll, c_ll, c_ll, c_ll, c_int, c_int, c_int, c_int,
                                  c_int, c_float, P]),
+    't2v_op_attention_hd': (c_int, [P, P, P, P, c_ll, c_ll, c_ll, c_ll, c_ll, c_ll, c_ll, c_ll, c_int, c_int, c_int, c_int,
+                                    c_int, c_int, c_float, P]),
+    't2v_op_attention_relpos': (c_int, [P, P, P, P, P, P, c_ll, c_ll, c_ll, c_ll, c_ll, c_ll, c_ll, c_ll, c_int, c_int,
+                                        c_int, c_int, c_float, P]),
     't2v_op_upsample2x': (c_int, [P, P, c_int, c_int, c_int, c_int, P]),
     't2v_op_im2col_s2': (c_int, [P, P, c_int, c_int, c_int, c_int, P]),
     't2v_op_time_sinusoid': (c_int, [P, P, c_int, c_int, P]),

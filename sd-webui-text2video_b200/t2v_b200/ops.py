@@ -106,3 +106,26 @@ def attention(q, k, v, o, q_bs, q_ss, k_bs, k_ss, v_bs, v_ss, o_bs, o_ss, batch,
                             o_ss, batch, heads, sq, skv, kv_batch_div, scale, _lib.stream_ptr())
     _lib.check(rc, 'op_attention')
     return o
+
+
+def attention_hd(q, k, v, o, q_bs, q_ss, k_bs, k_ss, v_bs, v_ss, o_bs, o_ss, batch, heads, head_dim, sq, skv, kv_batch_div=1,
+                 scale=None):
+    """softmax(QK^T * scale)V for any supported head_dim (head h at column h*head_dim of the token matrices)."""
+    l = _lib.lib()
+    scale = head_dim ** -0.5 if scale is None else scale
+    rc = l.t2v_op_attention_hd(_lib.ptr(q), _lib.ptr(k), _lib.ptr(v), _lib.ptr(o), q_bs, q_ss, k_bs, k_ss, v_bs, v_ss, o_bs,
+                               o_ss, batch, heads, head_dim, sq, skv, kv_batch_div, scale, _lib.stream_ptr())
+    _lib.check(rc, 'op_attention_hd')
+    return o
+
+
+def attention_relpos(q, k, v, o, table_k, table_v, n_seq, seq_inner, bs_outer, bs_inner, ss, o_bs_outer, o_bs_inner, o_ss,
+                     heads, head_dim, T, max_rel, scale=None):
+    """Temporal self-attention with relative-position key / value tables (VideoCrafter TemporalCrossAttention)."""
+    l = _lib.lib()
+    scale = head_dim ** -0.5 if scale is None else scale
+    rc = l.t2v_op_attention_relpos(_lib.ptr(q), _lib.ptr(k), _lib.ptr(v), _lib.ptr(o), _lib.ptr(table_k), _lib.ptr(table_v),
+                                   n_seq, seq_inner, bs_outer, bs_inner, ss, o_bs_outer, o_bs_inner, o_ss, heads, head_dim, T,
+                                   max_rel, scale, _lib.stream_ptr())
+    _lib.check(rc, 'op_attention_relpos')
+    return o

@@ -181,6 +181,51 @@ def test_attention_tcgen05_shared_kv_and_peaked_scores(ops):
     assert rel(o, ref) < 3e-3
 
 
+@pytest.mark.parametrize('hd', [8, 16, 32, 40, 80, 160])
+@pytest.mark.parametrize('S,skv', [(256, 256), (100, 77), (1024, 1024)])
+def test_attention_other_head_dims(ops, hd, S, skv):
+    """VideoCrafter heads (C/8 = 40 / 80 / 160, and the tiny-config widths): spatial self- and CLIP cross-attention."""
+    batch, heads = 3, 8
+    if S == 1024 and hd not in (40, 160):
+        pytest.skip('large case only for the production widths')
+    C = heads * hd
+    q = torch.randn(batch, S, C, device=dev).half()
+    k = torch.randn(batch, skv, C, device=dev).half()
+    v = torch.randn(batch, skv, C, device=dev).half()
+    o = torch.zeros_like(q)
+    ops.attention_hd(q, k, v, o, S * C, C, skv * C, C, skv * C, C, S * C, C, batch, heads, hd, S, skv)
+
+    def sp(t):
+        return t.float().view(t.shape[0], t.shape[1], heads, hd).permute(0, 2, 1, 3)
+    ref = F.scaled_dot_product_attention(sp(q), sp(k), sp(v)).permute(0, 2, 1, 3).reshape(batch, S, C)
+    assert rel(o, ref) < 3e-3
+
+
+@pytest.mark.parametrize('hd,T,L', [(40, 16, 16), (80, 16, 16), (160, 16, 16), (8, 4, 4), (32, 4, 4), (16, 7, 9), (40, 12, 16)])
+def test_attention_relative_position_temporal(ops, hd, T, L):
+    """TemporalCrossAttention with RelativePosition tables (videocrafter attention_temporal.py:107-144) on the token
+    matrix [(b, f, p), 3C]: sequences run along frames for every pixel, no rearrange copies."""
+    B, P, heads = 2, 24, 8
+    C = heads * hd
+    qkv = torch.randn(B * T * P, 3 * C, device=dev).half()
+    tk = (torch.randn(2 * L + 1, hd, device=dev) * 0.5).half()
+    tv = (torch.randn(2 * L + 1, hd, device=dev) * 0.5).half()
+    o = torch.zeros(B * T * P, C, device=dev, dtype=torch.half)
+    ld = 3 * C
+    ops.attention_relpos(qkv, qkv[:, C:], qkv[:, 2 * C:], o, tk, tv, B * P, P, T * P * ld, ld, P * ld, T * P * C, C, P * C,
+                         heads, hd, T, L)
+    t = qkv.float().view(B, T, P, 3, heads, hd).permute(3, 0, 2, 4, 1, 5)       # [3, B, P, heads, T, hd]
+    q, k, v = t[0], t[1], t[2]
+    idx = (torch.arange(T, device=dev)[None, :] - torch.arange(T, device=dev)[:, None]).clamp(-L, L) + L
+    k2, v2 = tk.float()[idx], tv.float()[idx]                                       # [T, T, hd]
+    scale = hd ** -0.5
+    sim = (torch.einsum('bphtd,bphsd->bphts', q, k) + torch.einsum('bphtd,tsd->bphts', q, k2)) * scale
+    attn = sim.softmax(-1)
+    out = torch.einsum('bphts,bphsd->bphtd', attn, v) + torch.einsum('bphts,tsd->bphtd', attn, v2)
+    ref = out.permute(0, 3, 1, 2, 4).reshape(B * T * P, C)                          # [(b, t, p), (h d)]
+    assert rel(o, ref) < 3e-3
+
+
 def test_attention_temporal_strides_on_token_matrix(ops):
     """Sequences along frames for every pixel of a [(f, p), 3C] fused qkv matrix -- no rearrange copies."""
     Fr, P, heads = 24, 64, 5
