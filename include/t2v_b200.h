@@ -42,6 +42,11 @@ typedef struct {
     int num_res_blocks;
     float attn_scales[8];
     int n_attn_scales;
+    int arch;              /* 0: ModelScope UNetSD (modelscope/t2v_model.py:98-501)
+                            * 1: VideoCrafter UNetModel (videocrafter/lvdm/models/modules/openaimodel3d.py:281-670; dim =
+                            *    model_channels, dim_mult = channel_mult, attn_scales = 1/attention_resolutions, head width =
+                            *    channels / num_heads (head_dim ignored), state_dict keys of `model.diffusion_model.*`) */
+    int temporal_length;   /* arch 1: RelativePosition(max_relative_position = temporal_length), tables [2*L+1, d] */
 } t2v_unet_config;
 
 int t2v_unet_create(const t2v_unet_config* cfg, t2v_unet** out);

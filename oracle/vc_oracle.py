@@ -312,7 +312,7 @@ def _res(W, b: VCBlock, x, emb):
     return x + h
 
 
-def _run(W, blk: List[VCBlock], h, emb, ctx, cfg: VCConfig):
+def _run(W, blk: List[VCBlock], h, emb, ctx, cfg: VCConfig, taps=None):
     for b in blk:
         if b.kind == 'conv':
             h = F.conv3d(h, W[b.prefix + '.weight'], W[b.prefix + '.bias'], padding=(0, 1, 1))
@@ -325,10 +325,12 @@ def _run(W, blk: List[VCBlock], h, emb, ctx, cfg: VCConfig):
         elif b.kind == 'up':
             h = F.interpolate(h, (h.shape[2], h.shape[3] * 2, h.shape[4] * 2), mode='nearest')
             h = F.conv3d(h, W[b.prefix + '.conv.weight'], W[b.prefix + '.conv.bias'], padding=(0, 1, 1))
+        if taps is not None:
+            taps[b.prefix] = h
     return h
 
 
-def vc_unet_forward(W: Dict[str, torch.Tensor], cfg: VCConfig, x, t, ctx):
+def vc_unet_forward(W: Dict[str, torch.Tensor], cfg: VCConfig, x, t, ctx, taps=None):
     """UNetModel.forward (openaimodel3d.py:632-670): x [B,4,T,h,w], t [B], ctx [B,77,context_dim] -> eps [B,4,T,h,w]."""
     L = vc_enumerate(cfg)
     emb = vc_timestep_embedding(t, cfg.model_channels)
@@ -337,12 +339,12 @@ def vc_unet_forward(W: Dict[str, torch.Tensor], cfg: VCConfig, x, t, ctx):
     hs = []
     h = x
     for blk in L.input_blocks:
-        h = _run(W, blk, h, emb, ctx, cfg)
+        h = _run(W, blk, h, emb, ctx, cfg, taps)
         hs.append(h)
-    h = _run(W, L.middle, h, emb, ctx, cfg)
+    h = _run(W, L.middle, h, emb, ctx, cfg, taps)
     for blk in L.output_blocks:
         h = torch.cat([h, hs.pop()], dim=1)
-        h = _run(W, blk, h, emb, ctx, cfg)
+        h = _run(W, blk, h, emb, ctx, cfg, taps)
     h = F.silu(_gn(W, 'out.0', h, 1e-5))
     return F.conv3d(h, W['out.2.weight'], W['out.2.bias'], padding=(0, 1, 1))
 

@@ -462,6 +462,7 @@ int attention_relpos(const RelposParams& p, cudaStream_t stream) {
         case 16: return launch_relpos<16>(p, stream);
         case 32: return launch_relpos<32>(p, stream);
         case 40: return launch_relpos<40>(p, stream);
+        case 64: return launch_relpos<64>(p, stream);
         case 80: return launch_relpos<80>(p, stream);
         case 160: return launch_relpos<160>(p, stream);
         default: return -1;

@@ -125,12 +125,17 @@ void Arena::reset(char* base, bool no_reuse) {
     peak_ = 0;
     free_.clear();
     live_.clear();
+    count_ = 0;
+    const char* lim = getenv("T2V_ARENA_REUSE_LIMIT");      // debugging aid: only the first N allocations may reuse freed blocks
+    limit_ = lim ? atol(lim) : -1;
 }
 
 char* Arena::alloc(size_t bytes) {
     bytes = (bytes + 1023) & ~static_cast<size_t>(1023);
     if (bytes == 0) bytes = 1024;
-    if (!no_reuse_) {
+    const long idx = count_++;
+    if (getenv("T2V_ARENA_TRACE") && base_ != nullptr) fprintf(stderr, "[arena] alloc #%ld %zu bytes\n", idx, bytes);
+    if (!no_reuse_ && (limit_ < 0 || idx < limit_)) {
         int best = -1;
         for (int i = 0; i < static_cast<int>(free_.size()); ++i)
             if (free_[i].size >= bytes && (best < 0 || free_[i].size < free_[best].size)) best = i;
@@ -208,6 +213,10 @@ int Builder::gemm(GemmProblem& p) {
         const long long tiles = tiles_m * ((p.N + 255) / 256);
         const int kt = p.ntaps * ((p.K + GEMM_BLOCK_K - 1) / GEMM_BLOCK_K);
         int S = static_cast<int>(std::min<long long>(std::min<long long>(sms_ / std::max<long long>(tiles, 1), kt / 4), 8));
+        if (S >= 2) {       // the kernel never runs empty splits: use the split count gemm_plan will actually produce, the
+            const int kps = (kt + S - 1) / S;      // fix-up pass must not read partials nobody wrote
+            S = (kt + kps - 1) / kps;
+        }
         // (64-wide tiles without split-K were measured equal within 0.3 % on the whole forward: same MMA time per CTA)
         if (tiles * 2 <= sms_ && S >= 2) {
             const long long nrows = static_cast<long long>(rows);

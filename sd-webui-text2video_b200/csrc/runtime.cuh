@@ -56,11 +56,13 @@ public:
     char* alloc(size_t bytes);
     void free(char* p);
     size_t peak() const { return peak_; }
+    long count() const { return count_; }
 
 private:
     struct Blk { size_t off, size; };
     char* base_ = nullptr;
     bool no_reuse_ = false;
+    long count_ = 0, limit_ = -1;
     size_t top_ = 0, peak_ = 0;
     std::vector<Blk> free_;
     std::map<size_t, size_t> live_;

@@ -20,7 +20,7 @@ namespace t2v {
 namespace {
 
 struct Blk {
-    enum Kind { STEM, RES, ST, TT, DOWN, UP } kind;
+    enum Kind { STEM, RES, ST, TT, DOWN, UP, STT } kind;     // STT: VideoCrafter SpatialTemporalTransformer
     std::string prefix;
     int cin = 0, cout = 0, heads = 0, inner = 0;
 };
@@ -215,6 +215,126 @@ void expect_params(t2v_unet* u) {
     P.expect("out.2.bias", {c.out_dim});
 }
 
+
+// ---- VideoCrafter (arch 1): mirrors UNetModel.__init__ (videocrafter/lvdm/models/modules/openaimodel3d.py:407-617) with
+// legacy = False, num_head_channels = -1 (dim_head = ch / num_heads), resblock_updown = False, kernel_size_t = 1
+void enumerate_vc(t2v_unet* u) {
+    const t2v_unet_config& c = u->cfg;
+    const int mc = c.dim, nm = c.n_mult;
+    auto name = [](const char* base, int n, int k) {
+        char buf[64];
+        snprintf(buf, sizeof(buf), "%s.%d.%d", base, n, k);
+        return std::string(buf);
+    };
+    u->ins.push_back({Blk{Blk::STEM, "input_blocks.0.0", c.in_dim, mc, 0, 0}});
+    std::vector<int> chans{mc};
+    int ch = mc;
+    float scale = 1.0f;
+    for (int level = 0; level < nm; ++level) {
+        for (int j = 0; j < c.num_res_blocks; ++j) {
+            const int n = static_cast<int>(u->ins.size());
+            std::vector<Blk> blk;
+            blk.push_back(Blk{Blk::RES, name("input_blocks", n, 0), ch, mc * c.dim_mult[level], 0, 0});
+            ch = mc * c.dim_mult[level];
+            if (in_scales(c, scale)) blk.push_back(Blk{Blk::STT, name("input_blocks", n, 1), ch, ch, c.num_heads, ch});
+            u->ins.push_back(blk);
+            chans.push_back(ch);
+        }
+        if (level != nm - 1) {
+            const int n = static_cast<int>(u->ins.size());
+            u->ins.push_back({Blk{Blk::DOWN, name("input_blocks", n, 0), ch, ch, 0, 0}});
+            chans.push_back(ch);
+            scale /= 2.0f;
+        }
+    }
+    u->mid = {Blk{Blk::RES, "middle_block.0", ch, ch, 0, 0}, Blk{Blk::STT, "middle_block.1", ch, ch, c.num_heads, ch},
+              Blk{Blk::RES, "middle_block.2", ch, ch, 0, 0}};
+    for (int level = nm - 1; level >= 0; --level) {
+        for (int i = 0; i < c.num_res_blocks + 1; ++i) {
+            const int n = static_cast<int>(u->outs.size());
+            const int ich = chans.back();
+            chans.pop_back();
+            std::vector<Blk> blk;
+            blk.push_back(Blk{Blk::RES, name("output_blocks", n, 0), ch + ich, mc * c.dim_mult[level], 0, 0});
+            ch = mc * c.dim_mult[level];
+            if (in_scales(c, scale))
+                blk.push_back(Blk{Blk::STT, name("output_blocks", n, static_cast<int>(blk.size())), ch, ch, c.num_heads, ch});
+            if (level != 0 && i == c.num_res_blocks) {
+                blk.push_back(Blk{Blk::UP, name("output_blocks", n, static_cast<int>(blk.size())), ch, ch, 0, 0});
+                scale *= 2.0f;
+            }
+            u->outs.push_back(blk);
+        }
+    }
+}
+
+void expect_params_vc(t2v_unet* u) {
+    ParamStore& P = u->params;
+    const t2v_unet_config& c = u->cfg;
+    const int E = c.dim * 4;
+    auto lin = [&](const std::string& p, int o, int i, bool bias = true) {
+        P.expect(p + ".weight", {o, i});
+        if (bias) P.expect(p + ".bias", {o});
+    };
+    auto norm = [&](const std::string& p, int ch) {
+        P.expect(p + ".weight", {ch});
+        P.expect(p + ".bias", {ch});
+    };
+    auto conv = [&](const std::string& p, int o, int i, int k) {
+        P.expect(p + ".weight", {o, i, 1, k, k});
+        P.expect(p + ".bias", {o});
+    };
+    lin("time_embed.0", E, c.dim);
+    lin("time_embed.2", E, E);
+    std::vector<Blk> all;
+    for (auto& b : u->ins) all.insert(all.end(), b.begin(), b.end());
+    all.insert(all.end(), u->mid.begin(), u->mid.end());
+    for (auto& b : u->outs) all.insert(all.end(), b.begin(), b.end());
+    for (const Blk& b : all) {
+        const std::string& p = b.prefix;
+        switch (b.kind) {
+            case Blk::STEM: conv(p, b.cout, b.cin, 3); break;
+            case Blk::RES:
+                norm(p + ".in_layers.0", b.cin);
+                conv(p + ".in_layers.2", b.cout, b.cin, 3);
+                lin(p + ".emb_layers.1", b.cout, E);
+                norm(p + ".out_layers.0", b.cout);
+                conv(p + ".out_layers.3", b.cout, b.cout, 3);
+                if (b.cin != b.cout) conv(p + ".skip_connection", b.cout, b.cin, 1);
+                break;
+            case Blk::STT: {
+                const int inner = b.inner, d = inner / b.heads;
+                norm(p + ".norm", b.cin);
+                conv(p + ".proj_in", inner, b.cin, 1);
+                conv(p + ".proj_out", b.cin, inner, 1);
+                const std::string t = p + ".transformer_blocks.0";
+                const char* att[4] = {"attn1", "attn2", "attn1_tmp", "attn2_tmp"};
+                for (int a = 0; a < 4; ++a) {
+                    const std::string ap = t + "." + att[a];
+                    const int kd = a == 1 ? c.context_dim : inner;
+                    lin(ap + ".to_q", inner, inner, false);
+                    lin(ap + ".to_k", inner, kd, false);
+                    lin(ap + ".to_v", inner, kd, false);
+                    lin(ap + ".to_out.0", inner, inner);
+                    if (a >= 2) {
+                        P.expect(ap + ".relative_position_k.embeddings_table", {2 * c.temporal_length + 1, d});
+                        P.expect(ap + ".relative_position_v.embeddings_table", {2 * c.temporal_length + 1, d});
+                    }
+                }
+                lin(t + ".ff.net.0.proj", inner * 8, inner);
+                lin(t + ".ff.net.2", inner, inner * 4);
+                for (int n = 1; n <= 5; ++n) norm(t + ".norm" + std::to_string(n), inner);
+                break;
+            }
+            case Blk::DOWN: conv(p + ".op", b.cout, b.cin, 3); break;
+            case Blk::UP: conv(p + ".conv", b.cout, b.cin, 3); break;
+            default: break;
+        }
+    }
+    norm("out.0", c.dim);
+    conv("out.2", c.out_dim, c.dim, 3);
+}
+
 // ------------------------------------------------------------------------------------------ plan construction
 struct Ctx : NetCtx {
     t2v_unet* u;
@@ -407,6 +527,150 @@ Tok res_block(Ctx& c, const Tok& x, const Blk& blk, int hcur, int wcur) {
     return y;
 }
 
+
+// ---- VideoCrafter blocks
+// ResBlock._forward (openaimodel3d.py:244-271): every GroupNorm32 takes its statistics over (C/32, T, H, W) of a sample
+// (5-D input, util.py:271-273); the convs are Conv3d (1,3,3) = per-frame 3x3; no temporal conv.
+Tok res_block_vc(Ctx& c, const Tok& x, const Blk& blk, int hcur, int wcur) {
+    const std::string& p = blk.prefix;
+    const long long P = static_cast<long long>(hcur) * wcur;
+    const int Co = blk.cout;
+    const int E = c.u->cfg.dim * 4;
+    __half* bias1 = reinterpret_cast<__half*>(c.b->alloc_bytes(static_cast<size_t>(c.B) * Co * sizeof(__half)));
+    {
+        const __half* we = prm(c, p + ".emb_layers.1.weight");
+        const __half* be = prm(c, p + ".emb_layers.1.bias");
+        const __half* bc = prm(c, p + ".in_layers.2.bias");
+        const __half* emb = c.emb;
+        const int B = c.B;
+        c.b->step([=](cudaStream_t s) { return small_linear(emb, E, we, be, bc, bias1, Co, B, Co, E, 1, s); });
+    }
+    Tok a = group_norm(c, x, p + ".in_layers.0", P * c.F, 1e-5f, true);
+    Tok h = conv3x3(c, a, p + ".in_layers.2.weight", bias1, static_cast<int>(c.F * P), Co, Co, hcur, wcur, nullptr);
+    c.b->free(a);
+    Tok bn_ = group_norm(c, h, p + ".out_layers.0", P * c.F, 1e-5f, true);
+    c.b->free(h);
+    Tok skip = x;
+    bool own_skip = false;
+    if (blk.cin != blk.cout) {
+        skip = linear(c, x, prm(c, p + ".skip_connection.weight"), Co, prm(c, p + ".skip_connection.bias"), nullptr);
+        own_skip = true;
+    }
+    Tok h2 = conv3x3(c, bn_, p + ".out_layers.3.weight", prm(c, p + ".out_layers.3.bias"), 0, 0, Co, hcur, wcur, &skip);
+    c.b->free(bn_);
+    if (own_skip) c.b->free(skip);
+    c.b->free_bytes(bias1);
+    return h2;
+}
+
+// SpatialTemporalTransformer.forward (attention_temporal.py:386-399) around BasicTransformerBlockST._forward (:301-335):
+// spatial self -> temporal self (relative position) -> spatial cross (CLIP) -> temporal self again ("attn2_tmp" with
+// context None) -> GEGLU feed-forward, each with its own LayerNorm and a residual add.  All five run on the ONE token
+// matrix [(b, t, y, x), C]; the reference's five rearranges per block do not exist.
+Tok stt_block(Ctx& c, const Tok& xin, const Blk& blk, int hcur, int wcur) {
+    const std::string& p0 = blk.prefix;
+    const long long P = static_cast<long long>(hcur) * wcur;
+    const long long R = xin.rows;
+    const int C = blk.inner, heads = blk.heads, d = C / heads;
+    const float scale = 1.0f / std::sqrt(static_cast<float>(d));
+    Tok n = group_norm(c, xin, p0 + ".norm", P * c.F, 1e-6f, false);
+    Tok x = linear(c, n, prm(c, p0 + ".proj_in.weight"), C, prm(c, p0 + ".proj_in.bias"), nullptr);
+    c.b->free(n);
+    const std::string p = p0 + ".transformer_blocks.0";
+    auto finish = [&](Tok& o, Tok& qkv, const std::string& ap) {
+        c.b->free(qkv);
+        Tok y = linear(c, o, prm(c, ap + ".to_out.0.weight"), C, prm(c, ap + ".to_out.0.bias"), &x);
+        c.b->free(o);
+        c.b->free(x);
+        x = y;
+    };
+    auto spatial_self = [&](const std::string& ap, const std::string& lnp) {
+        const __half* wqkv = w_cat(c, {ap + ".to_q.weight", ap + ".to_k.weight", ap + ".to_v.weight"});
+        Tok qkv = ln_linear(c, x, lnp, ap + ".qkv", wqkv, nullptr, 3 * C, nullptr);
+        Tok o = c.b->alloc(R, C);
+        AttnParams a;
+        memset(&a, 0, sizeof(a));
+        a.q = qkv.p; a.k = qkv.p + C; a.v = qkv.p + 2 * C; a.o = o.p;
+        a.heads = heads; a.head_dim = d; a.scale = scale; a.kv_batch_div = 1; a.b_inner = 1;
+        a.batch = static_cast<int>(R / P);
+        a.sq = a.skv = static_cast<int>(P);
+        a.q_bs = a.k_bs = a.v_bs = P * qkv.ld;
+        a.q_ss = a.k_ss = a.v_ss = qkv.ld;
+        a.o_bs = P * o.ld;
+        a.o_ss = o.ld;
+        c.b->step([a](cudaStream_t s) { return a.head_dim == 64 ? attention(a, s) : attention_hd(a, s); }, 1, STEP_ATTN,
+                  4.0 * a.batch * a.heads * static_cast<double>(a.sq) * a.skv * d, "attn spatial (vc)");
+        finish(o, qkv, ap);
+    };
+    auto temporal = [&](const std::string& ap, const std::string& lnp) {
+        const __half* wqkv = w_cat(c, {ap + ".to_q.weight", ap + ".to_k.weight", ap + ".to_v.weight"});
+        Tok qkv = ln_linear(c, x, lnp, ap + ".qkv", wqkv, nullptr, 3 * C, nullptr);
+        Tok o = c.b->alloc(R, C);
+        RelposParams r;
+        memset(&r, 0, sizeof(r));
+        r.q = qkv.p; r.k = qkv.p + C; r.v = qkv.p + 2 * C; r.o = o.p;
+        r.table_k = prm(c, ap + ".relative_position_k.embeddings_table");
+        r.table_v = prm(c, ap + ".relative_position_v.embeddings_table");
+        r.n_seq = static_cast<long long>(c.B) * P;
+        r.seq_inner = P;
+        r.bs_outer = static_cast<long long>(c.F) * P * qkv.ld;
+        r.bs_inner = qkv.ld;
+        r.ss = P * qkv.ld;
+        r.o_bs_outer = static_cast<long long>(c.F) * P * o.ld;
+        r.o_bs_inner = o.ld;
+        r.o_ss = P * o.ld;
+        r.heads = heads; r.head_dim = d; r.T = c.F; r.max_rel = c.u->cfg.temporal_length; r.scale = scale;
+        const int nrel = 2 * r.max_rel + 1;
+        c.b->step([r](cudaStream_t s) { return attention_relpos(r, s); }, 1, STEP_ATTN,
+                  4.0 * r.n_seq * heads * static_cast<double>(c.F) * (c.F + nrel) * d, "attn temporal relpos (vc)");
+        finish(o, qkv, ap);
+    };
+    spatial_self(p + ".attn1", p + ".norm1");
+    temporal(p + ".attn1_tmp", p + ".norm4");
+    {   // spatial cross-attention on the prompt: K/V projected once per sample (the reference repeats the context per frame, :321-325)
+        const std::string ap = p + ".attn2";
+        Tok q = ln_linear(c, x, p + ".norm2", ap + ".to_q", prm(c, ap + ".to_q.weight"), nullptr, C, nullptr);
+        Tok ctx_tok;
+        ctx_tok.p = c.ctx;
+        ctx_tok.rows = static_cast<long long>(c.B) * c.L;
+        ctx_tok.C = c.u->cfg.context_dim;
+        ctx_tok.ld = ctx_tok.C;
+        const __half* wkv = w_cat(c, {ap + ".to_k.weight", ap + ".to_v.weight"});
+        Tok kv = linear(c, ctx_tok, wkv, 2 * C, nullptr, nullptr);
+        Tok o = c.b->alloc(R, C);
+        AttnParams a;
+        memset(&a, 0, sizeof(a));
+        a.q = q.p; a.k = kv.p; a.v = kv.p + C; a.o = o.p;
+        a.heads = heads; a.head_dim = d; a.scale = scale; a.b_inner = 1;
+        a.batch = static_cast<int>(R / P);
+        a.sq = static_cast<int>(P);
+        a.skv = c.L;
+        a.q_bs = P * q.ld; a.q_ss = q.ld;
+        a.k_bs = a.v_bs = static_cast<long long>(c.L) * kv.ld;
+        a.k_ss = a.v_ss = kv.ld;
+        a.kv_batch_div = c.F;
+        a.o_bs = P * o.ld; a.o_ss = o.ld;
+        c.b->step([a](cudaStream_t s) { return a.head_dim == 64 ? attention(a, s) : attention_hd(a, s); }, 1, STEP_ATTN,
+                  4.0 * a.batch * a.heads * static_cast<double>(a.sq) * a.skv * d, "attn cross (vc)");
+        c.b->free(kv);
+        finish(o, q, ap);
+    }
+    temporal(p + ".attn2_tmp", p + ".norm5");
+    {
+        const int H = 4 * C;
+        const int bn = (2 * H) % 256 == 0 ? 256 : ((2 * H) % 128 == 0 ? 128 : 64);
+        Geglu g = w_geglu(c, p + ".ff.net.0.proj", H, C, bn);
+        Tok gg = ln_linear(c, x, p + ".norm3", p + ".ff.net.0.proj#geglu" + std::to_string(bn), g.w, g.b, 2 * H, nullptr, GEMM_GEGLU, bn);
+        Tok y = linear(c, gg, prm(c, p + ".ff.net.2.weight"), C, prm(c, p + ".ff.net.2.bias"), &x);
+        c.b->free(gg);
+        c.b->free(x);
+        x = y;
+    }
+    Tok y = linear(c, x, prm(c, p0 + ".proj_out.weight"), blk.cin, prm(c, p0 + ".proj_out.bias"), &xin);
+    c.b->free(x);
+    return y;
+}
+
 Tok downsample(Ctx& c, const Tok& x, const Blk& blk, int hcur, int wcur) {
     const int frames = static_cast<int>(x.rows / (static_cast<long long>(hcur) * wcur));
     const int ho = (hcur + 1) / 2, wo = (wcur + 1) / 2;
@@ -489,7 +753,8 @@ int build(t2v_unet* u, Plan* plan, Arena* arena, bool dry, cudaStream_t stream, 
                 case Blk::STEM:
                     y = conv3x3(c, x, b.prefix + ".weight", prm(c, b.prefix + ".bias"), 0, 0, b.cout, hc, wc, nullptr);
                     break;
-                case Blk::RES: y = res_block(c, x, b, hc, wc); break;
+                case Blk::RES: y = cfg.arch == 1 ? res_block_vc(c, x, b, hc, wc) : res_block(c, x, b, hc, wc); break;
+                case Blk::STT: y = stt_block(c, x, b, hc, wc); break;
                 case Blk::ST: y = transformer(c, x, b, hc, wc, false); break;
                 case Blk::TT: y = transformer(c, x, b, hc, wc, true); break;
                 case Blk::DOWN:
@@ -540,7 +805,7 @@ int build(t2v_unet* u, Plan* plan, Arena* arena, bool dry, cudaStream_t stream, 
         run_block(blk);
     }
     // head: GN -> SiLU -> Conv3x3 dim -> out_dim (t2v_model.py:321-323)
-    Tok g = group_norm(c, x, "out.0", static_cast<long long>(hc) * wc, 1e-5f, true);
+    Tok g = group_norm(c, x, "out.0", static_cast<long long>(hc) * wc * (cfg.arch == 1 ? F : 1), 1e-5f, true);
     bld.free(x);
     Tok o = conv3x3(c, g, "out.2.weight", prm(c, "out.2.bias"), 0, 0, cfg.out_dim, hc, wc, nullptr, 16);
     bld.free(g);
@@ -587,7 +852,7 @@ Plan* get_plan(t2v_unet* u, int B, int F, int h, int w, int L, cudaStream_t stre
     IO io;
     {   // dry pass: peak activation bytes
         Plan scratch;
-        arena.reset(nullptr, u->taps_enabled);
+        arena.reset(nullptr, u->taps_enabled || getenv("T2V_ARENA_NO_REUSE") != nullptr);
         if (build(u, &scratch, &arena, true, stream, B, F, h, w, L, &io) != 0) return nullptr;
     }
     const size_t bytes = arena.peak() + (1 << 20);
@@ -596,7 +861,7 @@ Plan* get_plan(t2v_unet* u, int B, int F, int h, int w, int L, cudaStream_t stre
         return nullptr;
     }
     plan->slab_bytes = bytes;
-    arena.reset(plan->slab, u->taps_enabled);
+    arena.reset(plan->slab, u->taps_enabled || getenv("T2V_ARENA_NO_REUSE") != nullptr);
     if (build(u, plan.get(), &arena, false, stream, B, F, h, w, L, &io) != 0) return nullptr;
     plan->weights_version = u->params.version();
     Plan* raw = plan.get();
@@ -612,7 +877,7 @@ extern "C" {
 
 int t2v_unet_create(const t2v_unet_config* cfg, t2v_unet** out) {
     if (!cfg || !out) return -1;
-    if (cfg->head_dim != 64) {
+    if (cfg->arch == 0 && cfg->head_dim != 64) {
         set_error("head_dim must be 64 (got %d)", cfg->head_dim);
         return -2;
     }
@@ -620,10 +885,24 @@ int t2v_unet_create(const t2v_unet_config* cfg, t2v_unet** out) {
         set_error("dim must be a multiple of 64 and context_dim of 8");
         return -2;
     }
+    if (cfg->arch == 1 && (cfg->num_heads < 1 || (cfg->dim / cfg->num_heads) % 8 != 0 || cfg->temporal_length < 1 ||
+                           2 * cfg->temporal_length + 1 > 48)) {
+        set_error("VideoCrafter UNetModel: head width dim/num_heads must be a multiple of 8 and temporal_length <= 23");
+        return -2;
+    }
+    if (cfg->arch != 0 && cfg->arch != 1) {
+        set_error("unknown arch %d", cfg->arch);
+        return -2;
+    }
     t2v_unet* u = new t2v_unet();
     u->cfg = *cfg;
-    enumerate(u);
-    expect_params(u);
+    if (cfg->arch == 1) {
+        enumerate_vc(u);
+        expect_params_vc(u);
+    } else {
+        enumerate(u);
+        expect_params(u);
+    }
     *out = u;
     return 0;
 }
@@ -667,6 +946,10 @@ int t2v_unet_param_info(t2v_unet* u, int index, char* name_out, size_t name_cap,
 int t2v_unet_forward(t2v_unet* u, const void* x, int x_is_f32, const float* t, const void* ctx, void* out,
                      int out_is_f32, int B, int F, int h, int w, int L, void* stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    if (u->cfg.arch == 1 && (F > 16 || F - 1 > u->cfg.temporal_length)) {
+        set_error("VideoCrafter temporal attention kernel: frames must be <= min(16, temporal_length + 1) (got %d)", F);
+        return -4;
+    }
     Plan* plan = get_plan(u, B, F, h, w, L, stream);
     if (!plan) return -1;
     const IO& io = g_io[plan];

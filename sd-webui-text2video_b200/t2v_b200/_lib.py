@@ -62,7 +62,8 @@ SIGNATURES = {
 class UNetConfigC(C.Structure):
     _fields_ = [('in_dim', c_int), ('dim', c_int), ('context_dim', c_int), ('out_dim', c_int),
                 ('dim_mult', c_int * 8), ('n_mult', c_int), ('num_heads', c_int), ('head_dim', c_int),
-                ('num_res_blocks', c_int), ('attn_scales', c_float * 8), ('n_attn_scales', c_int)]
+                ('num_res_blocks', c_int), ('attn_scales', c_float * 8), ('n_attn_scales', c_int), ('arch', c_int),
+                ('temporal_length', c_int)]
 
 
 class VAEConfigC(C.Structure):

@@ -27,7 +27,17 @@ class _Holder(nn.Module):
     """Parameter-less container node (numeric child names are allowed by nn.Module)."""
 
 
-def _leaf_for(path, shapes, layer_norm_names=('norm1', 'norm2', 'norm3')):
+class _RelativePositionTable(nn.Module):
+    """Holds `embeddings_table` of videocrafter RelativePosition (attention_temporal.py:46-54)."""
+
+    def __init__(self, rows, units):
+        super().__init__()
+        self.embeddings_table = nn.Parameter(torch.zeros(rows, units))
+
+
+def _leaf_for(path, shapes, layer_norm_names=('norm1', 'norm2', 'norm3', 'norm4', 'norm5')):
+    if 'embeddings_table' in shapes:
+        return _RelativePositionTable(*shapes['embeddings_table'])
     w = shapes['weight']
     has_bias = 'bias' in shapes
     if len(w) == 1:
@@ -243,6 +253,57 @@ class UNetSD(_NativeModule):
         if n != out.numel():
             raise RuntimeError(f'read_tap({name}): {n} vs {out.numel()}: {_lib.load_library().t2v_last_error().decode()}')
         return out
+
+
+class UNetModel(UNetSD):
+    """Drop-in for videocrafter/lvdm/models/modules/openaimodel3d.py::UNetModel as configured by
+    base_t2v/model_config.yaml:21-46 (constructor keywords of that file; state_dict keys of `model.diffusion_model.*`).
+    `forward(x, timesteps, context=...)` -> eps, x [B,4,T,h,w].  T <= 16 frames (temporal_length)."""
+
+    def __init__(self, image_size=32, in_channels=4, model_channels=320, out_channels=4, num_res_blocks=2,
+                 attention_resolutions=(4, 2, 1), dropout=0, channel_mult=(1, 2, 4, 4), conv_resample=True, dims=3,
+                 num_classes=None, use_checkpoint=False, use_fp16=False, num_heads=8, num_head_channels=-1,
+                 num_heads_upsample=-1, use_scale_shift_norm=False, resblock_updown=False, transformer_depth=1,
+                 context_dim=768, legacy=False, kernel_size_t=1, padding_t=0, use_temporal_transformer=True,
+                 temporal_length=16, use_relative_position=True, parameterization='eps', **unused):
+        nn.Module.__init__(self)
+        unsupported = dict(dims=(dims, 3), num_classes=(num_classes, None), num_head_channels=(num_head_channels, -1),
+                           use_scale_shift_norm=(use_scale_shift_norm, False), resblock_updown=(resblock_updown, False),
+                           transformer_depth=(transformer_depth, 1), legacy=(legacy, False), kernel_size_t=(kernel_size_t, 1),
+                           padding_t=(padding_t, 0), use_relative_position=(use_relative_position, True),
+                           conv_resample=(conv_resample, True))
+        for k, (got, want) in unsupported.items():
+            if got != want:
+                raise NotImplementedError(f'UNetModel({k}={got!r}): only the base_t2v configuration ({k}={want!r}) is built')
+        self.in_dim, self.dim, self.context_dim, self.out_dim = in_channels, model_channels, context_dim, out_channels
+        self.in_channels, self.model_channels, self.out_channels = in_channels, model_channels, out_channels
+        self.dim_mult, self.num_heads, self.num_res_blocks = list(channel_mult), num_heads, num_res_blocks
+        self.attention_resolutions, self.temporal_length = list(attention_resolutions), temporal_length
+        self.parameterization = parameterization
+        self.v_posterior = 0
+        self.dtype = torch.float16
+        cfg = _lib.UNetConfigC()
+        cfg.in_dim, cfg.dim, cfg.context_dim, cfg.out_dim = in_channels, model_channels, context_dim, out_channels
+        for i, m in enumerate(self.dim_mult):
+            cfg.dim_mult[i] = int(m)
+        cfg.n_mult = len(self.dim_mult)
+        cfg.num_heads, cfg.head_dim, cfg.num_res_blocks = num_heads, 0, num_res_blocks
+        for i, ds in enumerate(self.attention_resolutions):
+            cfg.attn_scales[i] = 1.0 / float(ds)
+        cfg.n_attn_scales = len(self.attention_resolutions)
+        cfg.arch, cfg.temporal_length = 1, temporal_length
+        l = _lib.load_library()
+        h = C.c_void_p()
+        _lib.check(l.t2v_unet_create(C.byref(cfg), C.byref(h)), 'unet_create (VideoCrafter)')
+        object.__setattr__(self, '_handle', h)
+        _build_tree(self, _param_table('t2v_unet_param_info', h))
+        self._init_native()
+
+    @torch.no_grad()
+    def forward(self, x, timesteps=None, time_emb_replace=None, context=None, features_adapter=None, y=None, **kwargs):
+        if time_emb_replace is not None or features_adapter is not None or y is not None:
+            raise NotImplementedError('time_emb_replace / features_adapter / class labels are not part of the base_t2v path')
+        return UNetSD.forward(self, x, timesteps, context)
 
 
 def _encoder_table(ch, ch_mult, num_res_blocks, in_channels, z_channels):

@@ -174,3 +174,87 @@ def test_gaussian_cfg_quirk_and_fp16_rounding():
     assert rc == 0
     ref = (u + 7.5 * (c - u)).float()          # torch evaluates this in fp16, op by op
     assert torch.equal(out.view(-1), ref)
+
+
+# ---------------------------------------------------------------------------------------- VideoCrafter
+from oracle import vc_oracle as VC  # noqa: E402
+
+
+def _vc_net(cfg, wseed):
+    from t2v_b200.modules import UNetModel
+    W = UO.make_weights(VC.vc_param_specs(cfg), seed=wseed)
+    net = UNetModel(model_channels=cfg.model_channels, context_dim=cfg.context_dim, temporal_length=cfg.temporal_length).half()
+    net.load_state_dict(W, strict=True)
+    return W, net.cuda().eval()
+
+
+@pytest.mark.parametrize('name', ['vc_unet_tiny', 'vc_unet_full'])
+def test_vc_unet_vs_reference_fixture(gold_dir, name):
+    """UNetModel.forward (openaimodel3d.py:632-670) through t2v_unet_forward(arch = 1) vs the reference's fp32 output."""
+    g = torch.load(os.path.join(gold_dir, name + '.pt'))
+    cfg = VC.VCConfig(**g['cfg'])
+    W, net = _vc_net(cfg, g['wseed'])
+    B = g['shape'][0]
+    x = torch.randn(g['shape'], generator=torch.Generator('cpu').manual_seed(g['x_seed']))
+    ctx = torch.randn((B, g['L'], cfg.context_dim), generator=torch.Generator('cpu').manual_seed(g['ctx_seed']))
+    out = net(x.cuda(), g['t'].cuda(), context=ctx.cuda())
+    e = errs(out, g['out'])
+    assert e[1] < 1e-2 and e[0] < 3e-2, e
+    assert torch.equal(out, net(x.cuda(), g['t'].cuda(), context=ctx.cuda()))      # graph replay, bit-reproducible
+
+
+@pytest.mark.parametrize('B,T,h,w', [(1, 4, 8, 16), (2, 3, 16, 8), (1, 5, 8, 8)])
+def test_vc_unet_shapes_vs_oracle(B, T, h, w):
+    cfg = VC.VCConfig(model_channels=64, context_dim=48, temporal_length=4)
+    W, net = _vc_net(cfg, 5)
+    Wh = {k: v.half().float() for k, v in W.items()}
+    g = torch.Generator().manual_seed(B * 10 + T)
+    x = torch.randn(B, 4, T, h, w, generator=g)
+    ctx = torch.randn(B, 9, 48, generator=g).half().float()
+    t = torch.randint(0, 1000, (B,), generator=g)
+    ref = VC.vc_unet_forward(Wh, cfg, x, t, ctx)
+    e = errs(net(x.cuda(), t.cuda(), context=ctx.cuda()), ref)
+    assert e[1] < 1e-2 and e[0] < 3e-2, e
+
+
+# ---------------------------------------------------------------------------------------- full-size regressions
+def test_full_modelscope_unet_vs_reference_fixture(gold_dir):
+    """The public 1.41 B-parameter configuration at BASELINE config 1 (4 frames x 128^2): reference fp32 output."""
+    from t2v_b200.modules import UNetSD
+    g = torch.load(os.path.join(gold_dir, 'unet_cfg1.pt'))
+    cfg = UO.UNetConfig()
+    W = UO.make_weights(UO.param_specs(cfg), seed=g['wseed'])
+    net = UNetSD().half()
+    net.load_state_dict(W, strict=True)
+    net = net.cuda().eval()
+    x, c, uc = synth_inputs(g['F'], g['h'], g['w'])
+    t = torch.tensor([g['t']]).cuda()
+    e = errs(net(x.cuda(), t, c.cuda()), g['eps_cond'])
+    assert e[1] < 1e-2 and e[0] < 3e-2, e
+    assert errs(net(x.cuda(), t, uc.cuda()), g['eps_uncond'])[1] < 1e-2
+
+
+def test_activation_arena_reuse_does_not_change_results(monkeypatch):
+    """Regression: the split-K fix-up pass once read partial sums of splits the GEMM never ran (stale arena bytes), which
+    only showed at shapes whose K-tile count is not a multiple of the requested split.  The forward must be bit-identical
+    with and without activation-buffer reuse."""
+    from t2v_b200.modules import UNetSD
+    from t2v_b200.synthetic import randomize_
+    with torch.device('cuda'):
+        net = UNetSD()
+    net = randomize_(net.half().cuda().eval(), seed=0)
+    for (B, Fr, h, w) in ((1, 4, 16, 16), (2, 3, 8, 24)):
+        x = torch.randn(B, 4, Fr, h, w, device='cuda')
+        y = torch.randn(B, 77, 1024, device='cuda')
+        t = torch.full((B,), 500.0, device='cuda')
+        outs = []
+        for no_reuse in (True, False):
+            if no_reuse:
+                monkeypatch.setenv('T2V_ARENA_NO_REUSE', '1')
+            else:
+                monkeypatch.delenv('T2V_ARENA_NO_REUSE', raising=False)
+            p = getattr(net.time_embed, '0').bias
+            p.data = p.data.clone()             # re-shipped parameter -> new weights version -> the plan is rebuilt
+            net.mark_dirty()
+            outs.append(net(x, t, y).clone())
+        assert torch.equal(outs[0], outs[1])
