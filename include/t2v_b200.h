@@ -146,8 +146,9 @@ int t2v_op_attention_hd(const void* q, const void* k, const void* v, void* o, lo
                         long long k_bs, long long k_ss, long long v_bs, long long v_ss, long long o_bs, long long o_ss,
                         int batch, int heads, int head_dim, int sq, int skv, int kv_batch_div, float scale, void* stream);
 /* TemporalCrossAttention.forward with RelativePosition tables (attention_temporal.py:46-65, :107-144), context = x:
- * sequences of T <= 16 frames; sequence s of n_seq lives at (s / seq_inner) * bs_outer + (s % seq_inner) * bs_inner, its
- * frames `ss` elements apart; head h at column h * head_dim; tables [2*max_rel+1, head_dim] fp16, T - 1 <= max_rel. */
+ * sequences of T <= 32 frames; sequence s of n_seq lives at (s / seq_inner) * bs_outer + (s % seq_inner) * bs_inner, its
+ * frames `ss` elements apart; head h at column h * head_dim; tables [2*max_rel+1, head_dim] fp16 (2*max_rel+1 <= 48),
+ * frame distances beyond +-max_rel use the end rows of the tables, as the reference's clamp. */
 int t2v_op_attention_relpos(const void* q, const void* k, const void* v, void* o, const void* table_k, const void* table_v,
                             long long n_seq, long long seq_inner, long long bs_outer, long long bs_inner, long long ss,
                             long long o_bs_outer, long long o_bs_inner, long long o_ss, int heads, int head_dim, int T,

@@ -946,8 +946,8 @@ int t2v_unet_param_info(t2v_unet* u, int index, char* name_out, size_t name_cap,
 int t2v_unet_forward(t2v_unet* u, const void* x, int x_is_f32, const float* t, const void* ctx, void* out,
                      int out_is_f32, int B, int F, int h, int w, int L, void* stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-    if (u->cfg.arch == 1 && (F > 16 || F - 1 > u->cfg.temporal_length)) {
-        set_error("VideoCrafter temporal attention kernel: frames must be <= min(16, temporal_length + 1) (got %d)", F);
+    if (u->cfg.arch == 1 && F > 32) {
+        set_error("VideoCrafter temporal attention kernel: at most 32 frames per clip (got %d)", F);
         return -4;
     }
     Plan* plan = get_plan(u, B, F, h, w, L, stream);

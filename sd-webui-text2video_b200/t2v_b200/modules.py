@@ -258,7 +258,7 @@ class UNetSD(_NativeModule):
 class UNetModel(UNetSD):
     """Drop-in for videocrafter/lvdm/models/modules/openaimodel3d.py::UNetModel as configured by
     base_t2v/model_config.yaml:21-46 (constructor keywords of that file; state_dict keys of `model.diffusion_model.*`).
-    `forward(x, timesteps, context=...)` -> eps, x [B,4,T,h,w].  T <= 16 frames (temporal_length)."""
+    `forward(x, timesteps, context=...)` -> eps, x [B,4,T,h,w], T <= 32 frames."""
 
     def __init__(self, image_size=32, in_channels=4, model_channels=320, out_channels=4, num_res_blocks=2,
                  attention_resolutions=(4, 2, 1), dropout=0, channel_mult=(1, 2, 4, 4), conv_resample=True, dims=3,

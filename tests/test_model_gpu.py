@@ -203,8 +203,9 @@ def test_vc_unet_vs_reference_fixture(gold_dir, name):
     assert torch.equal(out, net(x.cuda(), g['t'].cuda(), context=ctx.cuda()))      # graph replay, bit-reproducible
 
 
-@pytest.mark.parametrize('B,T,h,w', [(1, 4, 8, 16), (2, 3, 16, 8), (1, 5, 8, 8)])
+@pytest.mark.parametrize('B,T,h,w', [(1, 4, 8, 16), (2, 3, 16, 8), (1, 5, 8, 8), (1, 9, 8, 8), (1, 24, 8, 8)])
 def test_vc_unet_shapes_vs_oracle(B, T, h, w):
+    # T > temporal_length + 1 = 5: relative positions clamp to the end rows of the tables (attention_temporal.py:60)
     cfg = VC.VCConfig(model_channels=64, context_dim=48, temporal_length=4)
     W, net = _vc_net(cfg, 5)
     Wh = {k: v.half().float() for k, v in W.items()}

@@ -201,7 +201,8 @@ def test_attention_other_head_dims(ops, hd, S, skv):
     assert rel(o, ref) < 3e-3
 
 
-@pytest.mark.parametrize('hd,T,L', [(40, 16, 16), (80, 16, 16), (160, 16, 16), (8, 4, 4), (32, 4, 4), (16, 7, 9), (40, 12, 16)])
+@pytest.mark.parametrize('hd,T,L', [(40, 16, 16), (80, 16, 16), (160, 16, 16), (8, 4, 4), (32, 4, 4), (16, 7, 9), (40, 12, 16),
+                                     (40, 24, 16), (80, 32, 16), (160, 24, 16), (16, 7, 3), (8, 20, 4), (64, 17, 16)])
 def test_attention_relative_position_temporal(ops, hd, T, L):
     """TemporalCrossAttention with RelativePosition tables (videocrafter attention_temporal.py:107-144) on the token
     matrix [(b, f, p), 3C]: sequences run along frames for every pixel, no rearrange copies."""

@@ -95,5 +95,5 @@ def test_errors_are_loud(ldm):
     with pytest.raises(RuntimeError):
         m.get_learned_conditioning(['a prompt'])                                   # no text tower attached
     with pytest.raises(RuntimeError):
-        m.model.diffusion_model(torch.randn(1, 4, 6, 8, 8).cuda(), torch.tensor([5]).cuda(),
-                                context=torch.randn(1, 9, 48).cuda())              # 6 frames > temporal_length + 1
+        m.model.diffusion_model(torch.randn(1, 4, 33, 8, 8).cuda(), torch.tensor([5]).cuda(),
+                                context=torch.randn(1, 9, 48).cuda())              # more than 32 frames per clip
