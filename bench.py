@@ -205,7 +205,7 @@ def run_b200(args):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for i in range(k):
-            r = fn(base_seed + i * world + rank)
+            r = fn(base_seed + i * n_units + unit)
             if with_gather:
                 gather(r)
         e1.record()
@@ -216,6 +216,8 @@ def run_b200(args):
             dist.barrier()
         return float(ms.item())
 
+    from t2v_b200 import distributed as D
+    unit, n_units = D.units()       # clip-rendering units: ranks (sample-DP) or rank pairs (T2V_CFG_SPLIT=1, distributed.py)
     W = max(args.warmup, 1)
     for i in range(W):
         clip_device(1000 + i)
@@ -225,10 +227,10 @@ def run_b200(args):
     ms = timed(clip_device, args.steps, 123, True)
     clk.stop_flag = True
     clk.join(timeout=2)
-    fps = world * args.steps * F / (ms / 1000.0)
+    fps = n_units * args.steps * F / (ms / 1000.0)
     clip_e2e(7)                                   # warm the e2e path (pinned staging, plan for B=2 already built)
     ms_e2e = timed(clip_e2e, args.steps, 123, False)
-    fps_e2e = world * args.steps * F / (ms_e2e / 1000.0)
+    fps_e2e = n_units * args.steps * F / (ms_e2e / 1000.0)
 
     if rank == 0:
         pk = peaks()
@@ -247,7 +249,8 @@ def run_b200(args):
             'ModelScope architecture, random CLIP-like conditioning)',
             'config': {'workload': f'ModelScope UNetSD {F}f x {H}x{Wd}, {S}-step {args.sampler}, cfg {args.cfg_scale}, batched '
                                    f'cond+uncond forward, + AutoencoderKL decode of {F} frames',
-                       'parallelism': f'sample-DP x{world} (one clip per GPU, one NCCL all-gather of the decoded clips)',
+                       'parallelism': (f'sample-DP x{world} (one clip per GPU, one NCCL all-gather of the decoded clips)' if n_units == world else
+                                       f'CFG-pair split: {n_units} pair(s) of GPUs, cond / uncond branch per GPU, one eps all-gather per step'),
                        'l2': 'inputs larger than L2: 2.8 GB of fp16 weights are re-read every forward, activations stream through a '
                              'multi-GB arena', 'flop_per_clip': clip_flops},
             'e2e': {'value': fps_e2e, 'unit': 'frames/s',

@@ -1,7 +1,15 @@
 """Sample-parallel sharding of clips over the GPUs of one node -- the only parallelism the reference has
 (videocrafter/sample_text2video.py:174-188 + lvdm/utils/dist_utils.py:4-19): every rank owns the full weights, draws its
 own noise from `seed + rank`, and ONE all-gather collects the decoded clips.  No collective touches the denoising
-loop, so scaling is weak.  Backend-agnostic (NCCL over NVLink on the B200 box, gloo in the CPU tests)."""
+loop, so scaling is weak.  Backend-agnostic (NCCL over NVLink on the B200 box, gloo in the CPU tests).
+
+Opt-in second mode (T2V_CFG_SPLIT=1, even world size): the classifier-free-guidance pair of every step -- two independent
+forwards, gaussian_sampler.py:161-162 / ddim/sampler.py:176-179 / ddim.py:216-217 -- is split over a PAIR of GPUs (even
+rank = conditional, odd rank = unconditional) with one all-gather of the two eps tensors per step (196 KB at 24f x 256^2)
+inside the pair; both ranks then apply the identical fused update, so the latent stays replicated.  This halves the
+latency of ONE clip (B = 1 forward per GPU instead of B = 2) at the cost of half the clips in flight; SURVEY.md 8e."""
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -28,3 +36,36 @@ def gather_clips(frames_u8):
     out = [torch.empty_like(frames_u8) for _ in range(ws)]
     dist.all_gather(out, frames_u8.contiguous())
     return out
+
+
+# ------------------------------------------------------------------------------------------------ CFG-pair split
+_pair_groups = None
+
+
+def cfg_split_enabled():
+    rank, ws = world()
+    return os.environ.get('T2V_CFG_SPLIT') == '1' and ws >= 2 and ws % 2 == 0
+
+
+def cfg_pair():
+    """(pair index, role, process group): role 0 evaluates the conditional branch, role 1 the unconditional one.
+    Every rank creates every pair group once (new_group is collective over the whole world)."""
+    global _pair_groups
+    rank, ws = world()
+    if _pair_groups is None:
+        _pair_groups = [dist.new_group([2 * i, 2 * i + 1]) for i in range(ws // 2)]
+    return rank // 2, rank % 2, _pair_groups[rank // 2]
+
+
+def units():
+    """(index, count) of the unit that renders whole clips: a rank in sample-DP mode, a rank pair in CFG-split mode."""
+    rank, ws = world()
+    return (rank // 2, ws // 2) if cfg_split_enabled() else (rank, ws)
+
+
+def exchange_eps(e_mine, group):
+    """All-gather of the two branches inside the pair -> (eps_cond, eps_uncond) on both ranks."""
+    e_mine = e_mine.contiguous()
+    out = [torch.empty_like(e_mine), torch.empty_like(e_mine)]
+    dist.all_gather(out, e_mine, group=group)
+    return out[0], out[1]

@@ -24,6 +24,7 @@ import numpy as np
 import torch
 
 from . import _lib
+from . import distributed as _dist
 from .modules import UNetSD
 
 try:                                                    # inside the webui these exist; standalone they do not
@@ -60,7 +61,11 @@ def _f32(v):
 
 
 def _eval_pair(model, x, t, c, uc):
-    """(eps_cond, eps_uncond).  One B=2 forward for our UNetSD with a single-sample latent, else two calls."""
+    """(eps_cond, eps_uncond).  One B=2 forward for our UNetSD with a single-sample latent, else two calls; in CFG-split
+    mode (distributed.py) this rank evaluates ONE branch and the pair exchanges the results."""
+    if _dist.cfg_split_enabled():
+        _, role, grp = _dist.cfg_pair()
+        return _dist.exchange_eps(model(x, t, c if role == 0 else uc), grp)
     if isinstance(model, UNetSD) and x.shape[0] == 1 and torch.is_tensor(c) and torch.is_tensor(uc) \
             and c.shape == uc.shape:
         xb = x.expand(2, *x.shape[1:])

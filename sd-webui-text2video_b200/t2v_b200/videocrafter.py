@@ -26,6 +26,7 @@ import torch.nn as nn
 from .modules import UNetModel, AutoencoderKL
 from .samplers import _step_kernel, _f32, _need_cuda
 from .distributed import gather_clips
+from . import distributed as _dist
 
 VAE_DDCONFIG = dict(double_z=True, z_channels=4, resolution=256, in_channels=3, out_ch=3, ch=128, ch_mult=[1, 2, 4, 4],
                     num_res_blocks=2, attn_resolutions=[], dropout=0.0)                 # model_config.yaml:53-66
@@ -151,6 +152,9 @@ class DDIMSampler(object):
         """(e_t, e_t_uncond) of ddim.py:212-221 as ONE batched forward (the two evaluations are independent samples)."""
         c, uc = self._ctx(cond), self._ctx(uncond)
         b = x.shape[0]
+        if _dist.cfg_split_enabled():       # one branch per GPU of a pair, one all-gather of eps per step (distributed.py)
+            _, role, grp = _dist.cfg_pair()
+            return _dist.exchange_eps(self.model.apply_model(x, ts, c if role == 0 else uc), grp)
         if c.shape == uc.shape:
             out = self.model.apply_model(torch.cat([x, x], 0), torch.cat([ts, ts], 0), torch.cat([c, uc], 0))
             return out[:b], out[b:]

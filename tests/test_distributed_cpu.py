@@ -52,3 +52,38 @@ def test_single_process_paths():
     x = torch.zeros(2, 2, 2, 3, dtype=torch.uint8)
     assert D.gather_clips(x)[0] is x
     assert D.clips_for_rank(3, 0, 1) == [0, 1, 2]
+
+
+def _cfg_worker(rank, ws, port, q):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    os.environ['T2V_CFG_SPLIT'] = '1'
+    dist.init_process_group('gloo', rank=rank, world_size=ws)
+    from t2v_b200 import samplers
+    calls = []
+
+    def model(x, t, c):                     # stand-in denoiser: records which branch this rank evaluated
+        calls.append(float(c.mean()))
+        return x * 0.5 + c.mean()
+    x = torch.arange(24, dtype=torch.float32).reshape(1, 4, 3, 2, 1)
+    c, uc = torch.full((1, 7, 8), 0.25), torch.full((1, 7, 8), -0.5)
+    e_c, e_u = samplers._eval_pair(model, x, torch.tensor([5]), c, uc)
+    q.put((rank, D.units(), calls, float((e_c - (x * 0.5 + 0.25)).abs().max()), float((e_u - (x * 0.5 - 0.5)).abs().max())))
+    dist.destroy_process_group()
+
+
+def test_cfg_pair_split_world2():
+    """CFG-split mode: each rank of a pair runs ONE branch, one all-gather gives both ranks (eps_cond, eps_uncond)."""
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_cfg_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res[0][1] == (0, 1) and res[1][1] == (0, 1)              # one clip-rendering unit (the pair)
+    assert res[0][2] == [0.25] and res[1][2] == [-0.5]              # even rank: conditional, odd rank: unconditional
+    assert all(r[3] == 0.0 and r[4] == 0.0 for r in res)
