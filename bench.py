@@ -153,6 +153,17 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def recorded_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per gemm_tc_kernel launch (bytes), from the committed ncu capture of the
+    434 GEMM launches of one forward (profiles/r01_gemm_dram_traffic.json); None when the file is absent.  A number taken
+    under ncu cannot be produced inside a timed run, so it is recorded, not live."""
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'r01_gemm_dram_traffic.json')) as f:
+            return float(json.load(f)['dram_bytes_per_launch'])
+    except Exception:
+        return None
+
+
 # --------------------------------------------------------------------------------------------- this repo
 def run_b200(args):
     import torch.distributed as dist
@@ -260,7 +271,7 @@ def run_b200(args):
             'clocks': clk.summary(),
             'achieved_tflops_whole_clip': clip_flops / (ms / args.steps * 1e-3) / 1e12,
             'roofline': {'bound': 'tensor', 'achieved': achieved, 'peak': pk['tflops_sustained'], 'unit': 'TFLOP/s',
-                         'frac': achieved / pk['tflops_sustained'], 'traffic': None, 'peak_source': pk['source'],
+                         'frac': achieved / pk['tflops_sustained'], 'traffic': recorded_traffic(), 'peak_source': pk['source'],
                          'kernel': 'gemm_tc_kernel (tcgen05 implicit GEMM), all launches of one B=2 forward, CUDA events per launch',
                          'gemm_share_of_forward': gemm['ms'] / prof['total_ms'] if prof['total_ms'] else None,
                          'forward_breakdown_ms': {k: round(v['ms'], 3) for k, v in prof.items() if isinstance(v, dict)}},
