@@ -25,6 +25,7 @@ enum GemmFlags : int {
     GEMM_OUT_F32 = 2,      // store fp32 instead of fp16
     GEMM_LN = 4,           // LayerNorm of the A rows folded into the epilogue: out = rstd_r * (acc - mean_r * colsum_n) + bias32_n
                            //   (weights pre-scaled by gamma; colsum_n = sum_k W'[n,k]; bias32_n = sum_k W[n,k] beta_k + bias_n)
+    GEMM_TMA_STORE = 8,    // set by gemm_plan: fp16 tile rows go through a swizzled smem staging buffer and cp.async.bulk.tensor stores
     // bring-up / performance-isolation switches (never set by the model code)
     GEMM_DBG_NO_STORE = 256,   // epilogue skips the global stores
     GEMM_DBG_NO_EPI = 512,     // epilogue releases the accumulator without reading it
@@ -56,6 +57,8 @@ struct GemmDesc {
     const float2* rowstat;           // GEMM_LN: (mean, rstd) per global row
     const float* colsum;             // GEMM_LN: per packed column
     const float* bias32;             // GEMM_LN: per packed column (replaces `bias`)
+    CUtensorMap map_out;             // GEMM_TMA_STORE: rank 1 + nd view of the output, box = (32 columns, 32 rows of a tile quadrant)
+    int8_t st_off[4][GEMM_MAX_RDIMS]; //   origin of quadrant q (rows 32q..32q+31 of the tile) inside the tile box
     int splits;                      // split-K: work item = (tile, split); each split owns k_per_split k-iterations and
     int k_per_split;                 //   stores its fp32 partial tile at out + split * split_stride (reduced by splitk_reduce)
     long long split_stride;
