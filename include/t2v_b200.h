@@ -110,6 +110,11 @@ int t2v_vae_param_info(t2v_vae* v, int index, char* name_out, size_t name_cap, i
  *   out_mode 1: uint8   [B*F, 8h, 8w, 3] RGB, tensor2vid arithmetic (t2v_pipeline.py:447-460)          */
 int t2v_vae_decode(t2v_vae* v, const void* z, int z_is_f32, float z_scale, void* out, int out_mode, int B, int F, int h,
                    int w, void* stream);
+/* moments = quant_conv(Encoder(x)) of AutoencoderKL.encode (modelscope/t2v_model.py:1640-1644; ldm Encoder ≙
+ * videocrafter/lvdm/models/modules/autoencoder_modules.py:382-482): x [N, 3, H, W] fp16/fp32 in [-1, 1] (device) ->
+ * moments_out [N, 2*embed_dim, H/8, W/8] fp32 = (mean | logvar).  compute_latents (t2v_pipeline.py:148-194) keeps
+ * mean * 0.18215.  Needs the `encoder.*` / `quant_conv.*` parameters (optional for decode-only use). */
+int t2v_vae_encode(t2v_vae* v, const void* x, int x_is_f32, void* moments_out, int N, int H, int W, void* stream);
 double t2v_vae_flops(t2v_vae* v, int nframes, int h, int w);
 
 /* ------------------------------------------------------------------------------------------ sampler steps

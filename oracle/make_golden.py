@@ -336,11 +336,40 @@ def gold_vc_ddim():
     torch.save(out, os.path.join(GOLD, 'vc_ddim.pt'))
 
 
+def gold_vae_encode(m):
+    """AutoencoderKL.encode(...).mean (t2v_model.py:1640-1644; what compute_latents keeps, t2v_pipeline.py:181-183)."""
+    cfg = VO.VAEConfig()
+    ddconfig = {'double_z': True, 'z_channels': 4, 'resolution': 256, 'in_channels': 3, 'out_ch': 3, 'ch': 128,
+                'ch_mult': [1, 2, 4, 4], 'num_res_blocks': 2, 'attn_resolutions': [], 'dropout': 0.0}
+    torch.manual_seed(0)
+    ae = m.AutoencoderKL(ddconfig, 4, None).eval()
+    specs = VO.encoder_param_specs(cfg)
+    sd = ae.state_dict()
+    enc_keys = {k for k in sd if k.startswith('encoder.') or k.startswith('quant_conv.')}
+    assert enc_keys == set(specs), enc_keys ^ set(specs)
+    for k in specs:
+        assert tuple(sd[k].shape) == specs[k], k
+    W = UO.make_weights(specs, seed=5)
+    sd.update(W)
+    ae.load_state_dict(sd, strict=True)
+    x = torch.rand((2, 3, 64, 96), generator=torch.Generator('cpu').manual_seed(6)) * 2 - 1
+    with torch.no_grad():
+        post = ae.encode(x)
+    mom = VO.vae_encode_moments(W, cfg, x)
+    err = (mom[:, :4] - post.mean).abs().max().item()
+    print(f'[vae_encode] oracle-vs-reference max|d| = {err:.3e} (mean absmax {post.mean.abs().max().item():.3f})')
+    assert err <= 1e-5 * max(1.0, post.mean.abs().max().item())
+    assert torch.allclose(torch.clamp(mom[:, 4:], -30.0, 20.0), post.logvar, atol=1e-5)
+    torch.save({'wseed': 5, 'x_seed': 6, 'x_shape': (2, 3, 64, 96), 'mean': post.mean, 'logvar': post.logvar},
+               os.path.join(GOLD, 'vae_encode.pt'))
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     m = ref_shim.load_modelscope()
     gold_samplers()
     gold_vae(m)
+    gold_vae_encode(m)
     tiny = UO.UNetConfig(dim=64)
     keep = ['input_blocks.0.0', 'input_blocks.0.1', 'input_blocks.1.0', 'input_blocks.1.1', 'input_blocks.1.2',
             'input_blocks.3', 'input_blocks.4.0', 'input_blocks.11.0', 'middle_block.1', 'middle_block.3',

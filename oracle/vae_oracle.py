@@ -1,4 +1,4 @@
-"""TEST INFRASTRUCTURE ONLY -- CPU oracle for `AutoencoderKL.decode`.
+"""TEST INFRASTRUCTURE ONLY -- CPU oracle for `AutoencoderKL.decode` and `AutoencoderKL.encode`.
 
 Functional restatement of t2v_model.py:1646-1649 (post_quant_conv -> Decoder) where Decoder is the
 un-vendored `ldm.modules.diffusionmodules.model.Decoder` (third-party package "stablediffusion",
@@ -123,6 +123,73 @@ def vae_decode(W: Dict[str, torch.Tensor], cfg: VAEConfig, z, taps=None):
             taps[f'up{lvl}'] = h
     h = _swish(_gn(W, 'decoder.norm_out', h))
     return F.conv2d(h, W['decoder.conv_out.weight'], W['decoder.conv_out.bias'], padding=1)
+
+
+def encoder_param_specs(cfg: VAEConfig, in_channels: int = 3) -> Dict[str, Tuple[int, ...]]:
+    """Keys of the ldm Encoder (autoencoder_modules.py:382-446) with the `encoder.` prefix, plus quant_conv
+    (t2v_model.py:1603: Conv2d(2*z_channels, 2*embed_dim, 1))."""
+    s: Dict[str, Tuple[int, ...]] = {}
+
+    def conv(p, o, i, k):
+        s[p + '.weight'] = (o, i, k, k)
+        s[p + '.bias'] = (o,)
+
+    def norm(p, c):
+        s[p + '.weight'] = (c,)
+        s[p + '.bias'] = (c,)
+
+    def resnet(p, ci, co):
+        norm(p + '.norm1', ci)
+        conv(p + '.conv1', co, ci, 3)
+        norm(p + '.norm2', co)
+        conv(p + '.conv2', co, co, 3)
+        if ci != co:
+            conv(p + '.nin_shortcut', co, ci, 1)
+
+    conv('encoder.conv_in', cfg.ch, in_channels, 3)
+    nres = len(cfg.ch_mult)
+    in_mult = (1,) + tuple(cfg.ch_mult)
+    block_in = cfg.ch
+    for lvl in range(nres):
+        block_in = cfg.ch * in_mult[lvl]
+        block_out = cfg.ch * cfg.ch_mult[lvl]
+        for j in range(cfg.num_res_blocks):
+            resnet(f'encoder.down.{lvl}.block.{j}', block_in, block_out)
+            block_in = block_out
+        if lvl != nres - 1:
+            conv(f'encoder.down.{lvl}.downsample.conv', block_in, block_in, 3)
+    resnet('encoder.mid.block_1', block_in, block_in)
+    norm('encoder.mid.attn_1.norm', block_in)
+    for n in ('q', 'k', 'v', 'proj_out'):
+        conv(f'encoder.mid.attn_1.{n}', block_in, block_in, 1)
+    resnet('encoder.mid.block_2', block_in, block_in)
+    norm('encoder.norm_out', block_in)
+    conv('encoder.conv_out', 2 * cfg.z_channels, block_in, 3)
+    conv('quant_conv', 2 * cfg.embed_dim, 2 * cfg.z_channels, 1)
+    return s
+
+
+@torch.no_grad()
+def vae_encode_moments(W: Dict[str, torch.Tensor], cfg: VAEConfig, x):
+    """AutoencoderKL.encode t2v_model.py:1640-1644 up to the moments: Encoder.forward autoencoder_modules.py:448-482, then
+    quant_conv.  x [N,3,H,W] in [-1,1] -> moments [N, 2*embed_dim, H/8, W/8] = (mean | logvar); the latent the pipeline uses
+    is `mean * 0.18215` (t2v_pipeline.py:181-183).  Downsample (autoencoder_modules.py:183-195): pad (0,1,0,1), 3x3 stride 2."""
+    x = x.to(W['encoder.conv_in.weight'].dtype)
+    h = F.conv2d(x, W['encoder.conv_in.weight'], W['encoder.conv_in.bias'], padding=1)
+    nres = len(cfg.ch_mult)
+    for lvl in range(nres):
+        for j in range(cfg.num_res_blocks):
+            h = _resnet(W, f'encoder.down.{lvl}.block.{j}', h)
+        if lvl != nres - 1:
+            h = F.pad(h, (0, 1, 0, 1), mode='constant', value=0)
+            h = F.conv2d(h, W[f'encoder.down.{lvl}.downsample.conv.weight'], W[f'encoder.down.{lvl}.downsample.conv.bias'],
+                         stride=2, padding=0)
+    h = _resnet(W, 'encoder.mid.block_1', h)
+    h = _attn(W, 'encoder.mid.attn_1', h)
+    h = _resnet(W, 'encoder.mid.block_2', h)
+    h = _swish(_gn(W, 'encoder.norm_out', h))
+    h = F.conv2d(h, W['encoder.conv_out.weight'], W['encoder.conv_out.bias'], padding=1)
+    return F.conv2d(h, W['quant_conv.weight'], W['quant_conv.bias'])
 
 
 def tensor2vid_u8(video):

@@ -78,10 +78,11 @@ __global__ void upsample2x_kernel(const uint4* x, uint4* y, long long nframes, i
     }
 }
 
-__global__ void im2col_s2_kernel(const uint4* x, uint4* col, long long nframes, int h, int w, int C8) {
+__global__ void im2col_s2_kernel(const uint4* x, uint4* col, long long nframes, int h, int w, int C8, int pad_lo) {
     griddep_wait();
     griddep_launch_small();
-    const int ho = (h + 1) / 2, wo = (w + 1) / 2;      // floor((h + 2 - 3)/2) + 1
+    // pad_lo = 1: symmetric padding 1 (Conv2d stride 2 padding 1); pad_lo = 0: the ldm Downsample's pad (0,1,0,1) + padding 0
+    const int ho = pad_lo ? (h + 1) / 2 : h / 2, wo = pad_lo ? (w + 1) / 2 : w / 2;
     const long long n = nframes * ho * wo * 9 * C8;
     GRID_STRIDE(i, n) {
         const int c = static_cast<int>(i % C8);
@@ -92,8 +93,8 @@ __global__ void im2col_s2_kernel(const uint4* x, uint4* col, long long nframes, 
         t /= wo;
         const int yo = static_cast<int>(t % ho);
         const long long f = t / ho;
-        const int yi = 2 * yo + tap / 3 - 1;
-        const int xi = 2 * xo + tap % 3 - 1;
+        const int yi = 2 * yo + tap / 3 - pad_lo;
+        const int xi = 2 * xo + tap % 3 - pad_lo;
         uint4 v = make_uint4(0, 0, 0, 0);
         if (yi >= 0 && yi < h && xi >= 0 && xi < w) v = __ldg(x + ((f * h + yi) * w + xi) * C8 + c);
         col[i] = v;
@@ -436,11 +437,11 @@ int upsample2x(const __half* x, __half* y, int nframes, int h, int w, int C, cud
                                                             nframes, h, w, C / 8);
     return ok();
 }
-int im2col_s2(const __half* x, __half* col, int nframes, int h, int w, int C, cudaStream_t stream) {
+int im2col_s2(const __half* x, __half* col, int nframes, int h, int w, int C, cudaStream_t stream, int pad_lo) {
     if (C % 8) return -1;
-    const long long n = static_cast<long long>(nframes) * ((h + 1) / 2) * ((w + 1) / 2) * 9 * (C / 8);
+    const long long n = static_cast<long long>(nframes) * ((pad_lo ? (h + 1) / 2 : h / 2)) * ((pad_lo ? (w + 1) / 2 : w / 2)) * 9 * (C / 8);
     launch_pdl(im2col_s2_kernel, grid_for(n, 256), 256, 0, stream, reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(col),
-                                                           nframes, h, w, C / 8);
+                                                           nframes, h, w, C / 8, pad_lo);
     return ok();
 }
 int concat_cols(const __half* a, long long lda, int Ca, const __half* b, long long ldb, int Cb, __half* out,

@@ -78,7 +78,7 @@ int egress_latent(const __half* tok, long long ld, void* out, int out_is_f32, in
                   cudaStream_t stream);
 int upsample2x(const __half* x, __half* y, int nframes, int h, int w, int C, cudaStream_t stream);
 // 3x3 stride-2 pad-1 gather: x [n, h, w, C] -> col [n*ho*wo, 9*C] (tap-major, tap = ky*3+kx)
-int im2col_s2(const __half* x, __half* col, int nframes, int h, int w, int C, cudaStream_t stream);
+int im2col_s2(const __half* x, __half* col, int nframes, int h, int w, int C, cudaStream_t stream, int pad_lo = 1);
 int concat_cols(const __half* a, long long lda, int Ca, const __half* b, long long ldb, int Cb, __half* out,
                 long long ldo, long long rows, cudaStream_t stream);
 // sinusoidal_embedding(t, dim): out [B, dim] fp16 = [cos(t*f_i) | sin(t*f_i)], f_i = 10000^(-i/half)

@@ -77,8 +77,8 @@ int ParamStore::info(int index, std::string* name, std::vector<long long>* shape
     for (auto& kv : params_) {
         if (!kv.second.expected) continue;
         if (i == index) {
-            *name = kv.first;
-            *shape = kv.second.shape;
+            if (name) *name = kv.first;
+            if (shape) *shape = kv.second.shape;
             found = true;
         }
         ++i;

@@ -15,8 +15,10 @@ using namespace t2v;
 
 struct t2v_vae {
     t2v_vae_config cfg;
-    ParamStore params;
+    ParamStore params;          // decoder + post_quant_conv (the hot path: missing_params counts these)
+    ParamStore enc_params;      // encoder + quant_conv (vid2vid / img2vid latent preparation; optional)
     std::map<std::string, std::unique_ptr<Plan>> plans;
+    std::map<std::string, std::unique_ptr<Plan>> enc_plans;
     void* gn_ws = nullptr;
     size_t gn_ws_bytes = 0;
     ~t2v_vae() {
@@ -69,6 +71,44 @@ void expect_params(t2v_vae* v) {
     }
     norm("decoder.norm_out", block_in);
     conv("decoder.conv_out", c.out_ch, block_in, 3);
+}
+
+// ldm Encoder (autoencoder_modules.py:382-446) + quant_conv (t2v_model.py:1603)
+void expect_enc_params(t2v_vae* v) {
+    ParamStore& P = v->enc_params;
+    const t2v_vae_config& c = v->cfg;
+    auto conv = [&](const std::string& p, int o, int i, int k) {
+        P.expect(p + ".weight", {o, i, k, k});
+        P.expect(p + ".bias", {o});
+    };
+    auto norm = [&](const std::string& p, int ch) {
+        P.expect(p + ".weight", {ch});
+        P.expect(p + ".bias", {ch});
+    };
+    auto resnet = [&](const std::string& p, int ci, int co) {
+        norm(p + ".norm1", ci);
+        conv(p + ".conv1", co, ci, 3);
+        norm(p + ".norm2", co);
+        conv(p + ".conv2", co, co, 3);
+        if (ci != co) conv(p + ".nin_shortcut", co, ci, 1);
+    };
+    conv("encoder.conv_in", c.ch, 3, 3);
+    int block_in = c.ch;
+    for (int lvl = 0; lvl < c.n_mult; ++lvl) {
+        const int block_out = c.ch * c.ch_mult[lvl];
+        for (int j = 0; j < c.num_res_blocks; ++j) {
+            resnet("encoder.down." + std::to_string(lvl) + ".block." + std::to_string(j), block_in, block_out);
+            block_in = block_out;
+        }
+        if (lvl != c.n_mult - 1) conv("encoder.down." + std::to_string(lvl) + ".downsample.conv", block_in, block_in, 3);
+    }
+    resnet("encoder.mid.block_1", block_in, block_in);
+    norm("encoder.mid.attn_1.norm", block_in);
+    for (const char* n : {"q", "k", "v", "proj_out"}) conv(std::string("encoder.mid.attn_1.") + n, block_in, block_in, 1);
+    resnet("encoder.mid.block_2", block_in, block_in);
+    norm("encoder.norm_out", block_in);
+    conv("encoder.conv_out", 2 * c.z_channels, block_in, 3);
+    conv("quant_conv", 2 * c.embed_dim, 2 * c.z_channels, 1);
 }
 
 // ResnetBlock.forward (autoencoder_modules.py:207-228, temb None): x + conv2(swish(GN(conv1(swish(GN(x))))))
@@ -255,6 +295,135 @@ Plan* get_plan(t2v_vae* v, int frames, int h, int w, cudaStream_t stream) {
     return raw;
 }
 
+
+// AutoencoderKL.encode up to the moments (t2v_model.py:1640-1644; Encoder.forward autoencoder_modules.py:448-482):
+// frames [N,3,H,W] -> tokens -> conv_in -> per level 2 ResnetBlocks (+ Downsample: pad (0,1,0,1), 3x3 stride 2) -> mid
+// (ResnetBlock, AttnBlock, ResnetBlock) -> GN + swish -> conv_out -> quant_conv 1x1 -> (mean | logvar) tokens.
+struct EncIO {
+    __half* x_tok;
+    __half* out_tok;
+    int out_ld;
+    int ho, wo;
+};
+std::map<Plan*, EncIO> g_encio;
+
+int build_enc(t2v_vae* v, Plan* plan, Arena* arena, bool dry, cudaStream_t stream, int frames, int H, int W, EncIO* io) {
+    Builder bld(plan, arena, dry, num_sms());
+    NetCtx c{&v->enc_params, &bld, stream, v->gn_ws};
+    const t2v_vae_config& cfg = v->cfg;
+    int hc = H, wc = W;
+    Tok x0 = bld.alloc(static_cast<long long>(frames) * H * W, 8);          // RGB zero-padded to 8 channels
+    io->x_tok = x0.p;
+    Tok x = conv3x3(c, x0, "encoder.conv_in.weight", prm(c, "encoder.conv_in.bias"), 0, 0, cfg.ch, hc, wc, nullptr);
+    int block_in = cfg.ch;
+    for (int lvl = 0; lvl < cfg.n_mult; ++lvl) {
+        const int block_out = cfg.ch * cfg.ch_mult[lvl];
+        for (int j = 0; j < cfg.num_res_blocks; ++j) {
+            Tok y = resnet(c, x, "encoder.down." + std::to_string(lvl) + ".block." + std::to_string(j), block_out, hc, wc);
+            bld.free(x);
+            x = y;
+            block_in = block_out;
+        }
+        if (lvl != cfg.n_mult - 1) {
+            const int ho = hc / 2, wo = wc / 2;
+            Tok col = bld.alloc(static_cast<long long>(frames) * ho * wo, 9 * x.C);
+            {
+                const Tok xx = x;
+                const int hh = hc, ww = wc;
+                bld.step([=](cudaStream_t s) { return im2col_s2(xx.p, col.p, frames, hh, ww, xx.C, s, 0); });
+            }
+            const std::string dn = "encoder.down." + std::to_string(lvl) + ".downsample.conv";
+            const __half* w = w_conv_kmajor(c, dn + ".weight");
+            Tok y = linear(c, col, w, block_in, prm(c, dn + ".bias"), nullptr);
+            bld.free(col);
+            bld.free(x);
+            x = y;
+            hc = ho;
+            wc = wo;
+        }
+    }
+    Tok y = resnet(c, x, "encoder.mid.block_1", block_in, hc, wc);
+    bld.free(x);
+    x = y;
+    y = attn_block(c, x, "encoder.mid.attn_1", frames, hc, wc);
+    bld.free(x);
+    x = y;
+    y = resnet(c, x, "encoder.mid.block_2", block_in, hc, wc);
+    bld.free(x);
+    x = y;
+    Tok g = group_norm(c, x, "encoder.norm_out", static_cast<long long>(hc) * wc, 1e-6f, true);
+    bld.free(x);
+    const int M = 2 * cfg.z_channels;
+    Tok h = conv3x3(c, g, "encoder.conv_out.weight", prm(c, "encoder.conv_out.bias"), 0, 0, M, hc, wc, nullptr, 16);
+    bld.free(g);
+    Tok mom = bld.alloc(h.rows, 2 * cfg.embed_dim, round_up(2 * cfg.embed_dim, 8));
+    {
+        const __half* w = w_conv(c, "quant_conv.weight", 1, 16, static_cast<int>(h.ld));
+        GemmProblem pr = base_problem(h, static_cast<int>(h.ld), w, 16, 2 * cfg.embed_dim, mom);
+        pr.bias = prm(c, "quant_conv.bias");
+        bld.gemm(pr);
+    }
+    bld.free(h);
+    io->out_tok = mom.p;
+    io->out_ld = static_cast<int>(mom.ld);
+    io->ho = hc;
+    io->wo = wc;
+    return bld.error;
+}
+
+Plan* get_enc_plan(t2v_vae* v, int frames, int H, int W, cudaStream_t stream) {
+    char key[64];
+    snprintf(key, sizeof(key), "%d,%d,%d", frames, H, W);
+    auto it = v->enc_plans.find(key);
+    if (it != v->enc_plans.end() && it->second->weights_version == v->enc_params.version()) return it->second.get();
+    if (it != v->enc_plans.end()) {
+        g_encio.erase(it->second.get());
+        v->enc_plans.erase(it);
+    }
+    std::string miss;
+    if (v->enc_params.missing(&miss) > 0) {
+        set_error("VAE encoder parameters missing (e.g. '%s')", miss.c_str());
+        return nullptr;
+    }
+    {
+        size_t need = gn_workspace_bytes(H * W, frames, num_sms()) + (1 << 20);
+        if (need > v->gn_ws_bytes) {
+            if (v->gn_ws) cudaFree(v->gn_ws);
+            if (cudaMalloc(&v->gn_ws, need) != cudaSuccess) {
+                set_error("groupnorm workspace cudaMalloc failed");
+                return nullptr;
+            }
+            cudaMemsetAsync(v->gn_ws, 0, need, stream);
+            v->gn_ws_bytes = need;
+            v->plans.clear();
+            g_vio.clear();
+            v->enc_plans.clear();
+            g_encio.clear();
+        }
+    }
+    std::unique_ptr<Plan> plan(new Plan());
+    Arena arena;
+    EncIO io;
+    {
+        Plan scratch;
+        arena.reset(nullptr, false);
+        if (build_enc(v, &scratch, &arena, true, stream, frames, H, W, &io) != 0) return nullptr;
+    }
+    const size_t bytes = arena.peak() + (1 << 20);
+    if (cudaMalloc(&plan->slab, bytes) != cudaSuccess) {
+        set_error("VAE encoder activation slab cudaMalloc(%zu MB) failed", bytes >> 20);
+        return nullptr;
+    }
+    plan->slab_bytes = bytes;
+    arena.reset(plan->slab, false);
+    if (build_enc(v, plan.get(), &arena, false, stream, frames, H, W, &io) != 0) return nullptr;
+    plan->weights_version = v->enc_params.version();
+    Plan* raw = plan.get();
+    g_encio[raw] = io;
+    v->enc_plans[key] = std::move(plan);
+    return raw;
+}
+
 }  // namespace
 }  // namespace t2v
 
@@ -269,6 +438,7 @@ int t2v_vae_create(const t2v_vae_config* cfg, t2v_vae** out) {
     t2v_vae* v = new t2v_vae();
     v->cfg = *cfg;
     expect_params(v);
+    expect_enc_params(v);
     *out = v;
     return 0;
 }
@@ -276,12 +446,14 @@ int t2v_vae_create(const t2v_vae_config* cfg, t2v_vae** out) {
 void t2v_vae_destroy(t2v_vae* v) {
     if (!v) return;
     for (auto& kv : v->plans) g_vio.erase(kv.second.get());
+    for (auto& kv : v->enc_plans) g_encio.erase(kv.second.get());
     delete v;
 }
 
 int t2v_vae_set_param(t2v_vae* v, const char* name, const void* data, int dtype, int ndim, const int64_t* shape,
                       void* stream) {
-    return v->params.set(name, data, dtype, ndim, shape, reinterpret_cast<cudaStream_t>(stream));
+    const bool enc = strncmp(name, "encoder.", 8) == 0 || strncmp(name, "quant_conv.", 11) == 0;
+    return (enc ? v->enc_params : v->params).set(name, data, dtype, ndim, shape, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int t2v_vae_missing_params(t2v_vae* v, char* name_out, size_t name_cap) {
@@ -297,8 +469,13 @@ int t2v_vae_missing_params(t2v_vae* v, char* name_out, size_t name_cap) {
 int t2v_vae_param_info(t2v_vae* v, int index, char* name_out, size_t name_cap, int64_t* shape_out, int* ndim_out) {
     std::string name;
     std::vector<long long> shape;
-    const int n = v->params.info(index, &name, &shape);
-    if (n < 0) return -1;
+    // decoder-side parameters first, then the encoder's (same state_dict, t2v_model.py:1585-1617)
+    const int n_dec = v->params.info(0, nullptr, nullptr);
+    const int n_enc = v->enc_params.info(0, nullptr, nullptr);
+    if (index < 0 || index >= n_dec + n_enc) return -1;
+    if (index < n_dec) v->params.info(index, &name, &shape);
+    else v->enc_params.info(index - n_dec, &name, &shape);
+    const int n = n_dec + n_enc;
     if (name_out && name_cap > 0) {
         strncpy(name_out, name.c_str(), name_cap - 1);
         name_out[name_cap - 1] = 0;
@@ -334,6 +511,27 @@ int t2v_vae_decode(t2v_vae* v, const void* z, int z_is_f32, float z_scale, void*
         return frames_to_u8(io.out_tok, io.out_ld, reinterpret_cast<uint8_t*>(out), static_cast<long long>(frames) * Ho * Wo,
                             stream);
     return frames_to_f32_nchw(io.out_tok, io.out_ld, reinterpret_cast<float*>(out), frames, Ho, Wo, stream);
+}
+
+int t2v_vae_encode(t2v_vae* v, const void* x, int x_is_f32, void* moments_out, int N, int H, int W, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    int down = 1;
+    for (int i = 1; i < v->cfg.n_mult; ++i) down *= 2;
+    if (N < 1 || H % down != 0 || W % down != 0) {
+        set_error("t2v_vae_encode: H and W must be multiples of %d (got %d x %d)", down, H, W);
+        return -3;
+    }
+    Plan* plan = get_enc_plan(v, N, H, W, stream);
+    if (!plan) return -1;
+    const EncIO& io = g_encio[plan];
+    int rc = ingest_latent(x, x_is_f32, io.x_tok, 8, 8, N, 3, 1, H, W, 1.0f, stream);
+    if (rc != 0) return rc;
+    rc = run_plan(plan, stream, true);
+    if (rc != 0) {
+        set_error("VAE encoder launch failed (%d): %s", rc, cudaGetErrorString(cudaGetLastError()));
+        return rc;
+    }
+    return egress_latent(io.out_tok, io.out_ld, moments_out, 1, N, 2 * v->cfg.embed_dim, 1, io.ho, io.wo, stream);
 }
 
 double t2v_vae_flops(t2v_vae* v, int nframes, int h, int w) {

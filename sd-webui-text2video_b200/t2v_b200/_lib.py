@@ -35,6 +35,7 @@ SIGNATURES = {
     't2v_vae_missing_params': (c_int, [P, c_char_p, C.c_size_t]),
     't2v_vae_param_info': (c_int, [P, c_int, c_char_p, C.c_size_t, C.POINTER(C.c_int64), C.POINTER(c_int)]),
     't2v_vae_decode': (c_int, [P, P, c_int, c_float, P, c_int, c_int, c_int, c_int, c_int, P]),
+    't2v_vae_encode': (c_int, [P, P, c_int, P, c_int, c_int, c_int, P]),
     't2v_vae_flops': (c_double, [P, c_int, c_int, c_int]),
     't2v_ddim_step': (c_int, [P, P, P, c_int, P, c_ll, c_ll, c_int, c_int, c_float, c_int, c_float, c_float, c_float, c_float,
                               c_float, P, c_int, P]),

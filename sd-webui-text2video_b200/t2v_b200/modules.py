@@ -347,10 +347,33 @@ def _encoder_table(ch, ch_mult, num_res_blocks, in_channels, z_channels):
     return t
 
 
+class DiagonalGaussianDistribution(object):
+    """ldm.modules.distributions.distributions.DiagonalGaussianDistribution (vendored twin:
+    videocrafter/lvdm/models/modules/distributions.py:24-76): moments [N, 2C, h, w] -> mean, logvar clamped to [-30, 20]."""
+
+    def __init__(self, parameters, deterministic=False):
+        self.parameters = parameters
+        self.mean, self.logvar = torch.chunk(parameters, 2, dim=1)
+        self.logvar = torch.clamp(self.logvar, -30.0, 20.0)
+        self.deterministic = deterministic
+        self.std = torch.exp(0.5 * self.logvar)
+        self.var = torch.exp(self.logvar)
+        if deterministic:
+            self.var = self.std = torch.zeros_like(self.mean)
+
+    def sample(self, noise=None):
+        if noise is None:
+            noise = torch.randn(self.mean.shape, device=self.parameters.device)
+        return self.mean + self.std * noise.to(device=self.parameters.device)
+
+    def mode(self):
+        return self.mean
+
+
 class AutoencoderKL(_NativeModule):
-    """Drop-in for modelscope/t2v_model.py::AutoencoderKL (ctor :1587-1617).  decode() runs on the library; the
-    encoder's parameters are held so that VQGAN_autoencoder.pth loads strictly, but encode() (vid2vid / img2vid
-    preparation) is not on the hot path and not built yet."""
+    """Drop-in for modelscope/t2v_model.py::AutoencoderKL (ctor :1587-1617): decode() (the hot path) and encode()
+    (vid2vid / img2vid latent preparation) both run on the library; state_dict keys of
+    VQGAN_autoencoder.pth (`encoder.*`, `decoder.*`, `quant_conv.*`, `post_quant_conv.*`)."""
     _set_fn = 't2v_vae_set_param'
 
     def __init__(self, ddconfig, embed_dim, ckpt_path=None, **unused):
@@ -418,9 +441,24 @@ class AutoencoderKL(_NativeModule):
         self.load_state_dict({k.split('first_stage_model.')[-1]: v for k, v in sd.items()
                               if 'first_stage_model' in k}, strict=True)
 
+    @torch.no_grad()
     def encode(self, x):
-        raise NotImplementedError('AutoencoderKL.encode (vid2vid / img2vid latent preparation) is outside the '
-                                  'denoise+decode hot path built so far (SURVEY.md section 8f)')
+        """posterior = AutoencoderKL.encode(x) (t2v_model.py:1640-1644): x [N, 3, H, W] in [-1, 1] on the GPU -> a
+        DiagonalGaussianDistribution (mean / logvar / std / var, .mode(), .sample()) over the latent [N, 4, H/8, W/8]."""
+        self.sync_weights()
+        l = _lib.lib()
+        if x.dim() != 4 or x.shape[1] != 3:
+            raise ValueError('x must be [N, 3, H, W]')
+        if x.dtype not in (torch.float32, torch.float16):
+            x = x.float()
+        x = x.contiguous()
+        if not x.is_cuda:
+            raise RuntimeError('AutoencoderKL.encode: the input must be on the GPU (there is no CPU path in t2v_b200)')
+        N, _, H, W = x.shape
+        mom = torch.empty((N, 2 * self.embed_dim, H // self.upscale, W // self.upscale), device=x.device, dtype=torch.float32)
+        rc = l.t2v_vae_encode(self._handle, _lib.ptr(x), int(x.dtype == torch.float32), _lib.ptr(mom), N, H, W, _lib.stream_ptr())
+        _lib.check(rc, 'vae_encode')
+        return DiagonalGaussianDistribution(mom)
 
     @torch.no_grad()
     def decode(self, z):

@@ -110,6 +110,8 @@ class TextToVideoSynthesis(object):
         steps = steps - skip_steps
         c, uc = self.preprocess(prompt, n_prompt, steps)
         strength = None if (strength == 0.0 and not is_vid2vid) else strength
+        if latents is not None:
+            latents = latents.to(self.device)       # the reference's get_noise discards its `.to(device)` (samplers_common.py:106)
         latents, noise, shape = self.diffusion.get_noise(1, 4, frames, height, width, seed=seed, latents=latents)
         self.diffusion.get_sampler(sampler, return_sampler=False)
         x0 = self.diffusion.sample_loop(steps=steps, strength=strength, eta=eta, conditioning=c,
@@ -125,8 +127,20 @@ class TextToVideoSynthesis(object):
         video = [np.ascontiguousarray(f[:, :, ::-1]) for f in rgb]       # cv2.COLOR_RGB2BGR (t2v_pipeline.py:431-434)
         return video, self.last_tensor, create_infotext(prompt, n_prompt, vars_)
 
+    @torch.no_grad()
     def compute_latents(self, vd_out, cpu_vae='GPU (half precision)', device=None):
-        raise NotImplementedError('vid2vid latent preparation needs AutoencoderKL.encode (SURVEY.md section 8f row 2)')
+        """vid2vid / img2vid latent preparation (t2v_pipeline.py:148-194): vd_out [b, 3, f, H, W] in [-1, 1] ->
+        latents [b, 4, f, H/8, W/8] fp32 on the CPU = posterior.mean * 0.18215.  All frames are encoded in one batch
+        instead of the reference's chunk-of-one loop; `cpu_vae` variants other than the GPU ones raise (no CPU path)."""
+        if 'CPU' in cpu_vae:
+            raise RuntimeError('t2v_b200 has no CPU VAE path; use "GPU (half precision)"')
+        dev = device if device is not None else self.device
+        b, c, f, H, W = vd_out.shape
+        frames = vd_out.to(dev).permute(0, 2, 1, 3, 4).reshape(b * f, c, H, W)
+        frames = frames.half() if 'half precision' in cpu_vae else frames.float()
+        mean = self.autoencoder.encode(frames).mean * SCALE_FACTOR
+        lat = mean.reshape(b, f, *mean.shape[1:]).permute(0, 2, 1, 3, 4)
+        return lat.to(torch.float32).cpu()
 
 
 def create_infotext(prompt, n_prompt, params):

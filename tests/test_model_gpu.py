@@ -259,3 +259,33 @@ def test_activation_arena_reuse_does_not_change_results(monkeypatch):
             net.mark_dirty()
             outs.append(net(x, t, y).clone())
         assert torch.equal(outs[0], outs[1])
+
+
+# ---------------------------------------------------------------------------------------- VAE encode (vid2vid preparation)
+def test_vae_encode_vs_reference_fixture_and_compute_latents(gold_dir):
+    """AutoencoderKL.encode(x).mean (t2v_model.py:1640-1644) through t2v_vae_encode vs the reference's fp32 output, and
+    compute_latents (t2v_pipeline.py:148-194) on top of it."""
+    from t2v_b200.modules import AutoencoderKL
+    from t2v_b200.pipeline import VAE_DDCONFIG, TextToVideoSynthesis, SCALE_FACTOR
+    g = torch.load(os.path.join(gold_dir, 'vae_encode.pt'))
+    cfg = VO.VAEConfig()
+    W = {**UO.make_weights(VO.decoder_param_specs(cfg), seed=3), **UO.make_weights(VO.encoder_param_specs(cfg), seed=g['wseed'])}
+    ae = AutoencoderKL(VAE_DDCONFIG, 4, None).half()
+    ae.load_state_dict(W, strict=True)
+    ae = ae.cuda().eval()
+    x = torch.rand(g['x_shape'], generator=torch.Generator('cpu').manual_seed(g['x_seed'])) * 2 - 1
+    post = ae.encode(x.cuda())
+    e = errs(post.mean, g['mean'])
+    assert e[1] < 1e-2 and e[0] < 3e-2, e
+    assert errs(post.logvar, g['logvar'])[1] < 2e-2
+    assert post.sample(torch.zeros_like(post.mean)).equal(post.mode())
+    # frames with odd tile counts + fp32 input, vs the oracle on the fp16-rounded weights
+    Wh = {k: v.half().float() for k, v in W.items()}
+    x2 = torch.rand((3, 3, 40, 64), generator=torch.Generator('cpu').manual_seed(9)) * 2 - 1      # mid attention needs h*w % 8 == 0
+    ref = VO.vae_encode_moments(Wh, cfg, x2)
+    assert errs(ae.encode(x2.cuda()).parameters, ref)[1] < 1e-2
+    with pytest.raises(RuntimeError):
+        ae.encode(torch.zeros(1, 3, 36, 64).cuda())                      # H not a multiple of 8
+    # decode(encode(x)) runs end to end (round trip through both plans)
+    rec = ae.decode(post.mode())
+    assert rec.shape == (2, 3, 64, 96) and torch.isfinite(rec).all()

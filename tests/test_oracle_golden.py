@@ -134,3 +134,13 @@ def test_vc_ddim_matches_reference_fixture(gold_dir, S, scale, eta):
     o = VC.vc_ddim_sample(lambda xx, t, cc: analytic_model(xx, t, cc), SO.linear_sd_betas(), x, S, c, uc, scale, eta=eta,
                           noise_gen=torch.Generator('cpu').manual_seed(11))
     assert torch.allclose(o, g[f'S{S}_g{scale}_eta{eta}'], rtol=0, atol=1e-6)
+
+
+def test_vae_encode_matches_reference_fixture(gold_dir):
+    g = torch.load(os.path.join(gold_dir, 'vae_encode.pt'))
+    cfg = VO.VAEConfig()
+    W = UO.make_weights(VO.encoder_param_specs(cfg), seed=g['wseed'])
+    x = torch.rand(g['x_shape'], generator=torch.Generator('cpu').manual_seed(g['x_seed'])) * 2 - 1
+    mom = VO.vae_encode_moments(W, cfg, x)
+    assert torch.allclose(mom[:, :4], g['mean'], rtol=0, atol=1e-5)
+    assert torch.allclose(torch.clamp(mom[:, 4:], -30.0, 20.0), g['logvar'], rtol=0, atol=1e-5)

@@ -106,3 +106,28 @@ def test_process_modelscope_entry_point(pipe):
         pipe[0].infer('a cat', '', 3, 2, 1, 3.0, 64, 64)        # string prompts need a clip_encoder
     with pytest.raises(RuntimeError):
         pipe[0].infer(c, uc, 3, 2, 1, 3.0, 64, 64, 0.0, 'CPU (Low VRAM)')
+
+
+@pytest.mark.parametrize('sampler', ['DDIM_Gaussian', 'DDIM', 'UniPC'])
+def test_vid2vid_through_the_entry_point(pipe, sampler):
+    """vid2vid: input frames -> compute_latents (AutoencoderKL.encode on the library) -> encode_latent -> denoise -> decode
+    (process_modelscope.py:118-221 minus the file reading)."""
+    from t2v_b200 import process_modelscope as pm
+    p = pipe[0]
+    Wenc = UO.make_weights(VO.encoder_param_specs(VO.VAEConfig()), seed=5)
+    p.autoencoder.load_state_dict(Wenc, strict=False)
+    p.autoencoder.cuda()
+    pm.pipe = p
+    c, uc = conds()
+    vid = torch.rand((1, 3, 3, 64, 64), generator=torch.Generator().manual_seed(4)) * 2 - 1
+    lat = p.compute_latents(vid, 'GPU (half precision)', torch.device('cuda'))
+    assert lat.shape == (1, 4, 3, 8, 8) and lat.dtype == torch.float32 and not lat.is_cuda and torch.isfinite(lat).all()
+    base = dict(prompt_embeds=c, n_prompt_embeds=uc, steps=6, frames=3, seed=11, cfg_scale=5.0, width=64, height=64,
+                sampler=sampler)
+    out = pm.process_modelscope(dict(base, do_vid2vid=True, vid2vid_frames_tensor=vid, strength=0.5))
+    txt = pm.process_modelscope(dict(base))
+    assert len(out) == 1 and len(out[0]) == 3 and out[0][0].shape == (64, 64, 3)
+    assert any((a != b).any() for a, b in zip(out[0], txt[0]))          # the input video steers the result
+    with pytest.raises(NotImplementedError):
+        pm.process_modelscope(dict(base, do_vid2vid=True))                # no frames given: file reading is webui plumbing
+    pm.pipe = None
