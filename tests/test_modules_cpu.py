@@ -82,3 +82,39 @@ def test_mirror_against_reference_classes():
     rv = m.AutoencoderKL(dict(VAE_DDCONFIG), 4, None)
     mv = AutoencoderKL(VAE_DDCONFIG, 4)
     assert {k: tuple(v.shape) for k, v in rv.state_dict().items()} == {k: tuple(v.shape) for k, v in mv.state_dict().items()}
+
+
+# ---------------------------------------------------------------------------------------- VideoCrafter mirrors
+def test_videocrafter_unet_state_dict_layout():
+    from oracle import vc_oracle as VC
+    from t2v_b200.modules import UNetModel
+    for kw, cfg in ((dict(model_channels=64, context_dim=48, temporal_length=4),
+                     VC.VCConfig(model_channels=64, context_dim=48, temporal_length=4)), (dict(), VC.VCConfig())):
+        net = UNetModel(**kw)
+        specs = VC.vc_param_specs(cfg)
+        assert {k: tuple(v.shape) for k, v in net.state_dict().items()} == {k: tuple(v) for k, v in specs.items()}
+    mods = dict(net.named_modules())
+    assert isinstance(mods['input_blocks.1.0.in_layers.2'], nn.Conv3d)                                   # (1,3,3) kernels
+    assert mods['input_blocks.1.0.in_layers.2'].weight.shape == (320, 320, 1, 3, 3)
+    assert isinstance(mods['input_blocks.1.1.transformer_blocks.0.norm5'], nn.LayerNorm)
+    assert isinstance(mods['input_blocks.1.1.transformer_blocks.0.attn2.to_k'], nn.Linear)
+    assert mods['input_blocks.1.1.transformer_blocks.0.attn2.to_k'].weight.shape == (320, 768)
+    assert mods['input_blocks.1.1.transformer_blocks.0.attn1_tmp.relative_position_k'].embeddings_table.shape == (33, 40)
+    with pytest.raises(NotImplementedError):
+        UNetModel(use_scale_shift_norm=True)
+
+
+def test_videocrafter_latent_diffusion_layout_and_schedule():
+    from t2v_b200.videocrafter import LatentDiffusion, DDIMSampler, make_model_input_shape
+    m = LatentDiffusion(unet_config=dict(model_channels=64, context_dim=48, temporal_length=4), image_size=[8, 8], video_length=4)
+    keys = set(m.state_dict())
+    assert any(k.startswith('model.diffusion_model.input_blocks.') for k in keys)
+    assert 'first_stage_model.encoder.conv_in.weight' in keys and 'first_stage_model.post_quant_conv.bias' in keys
+    assert make_model_input_shape(m, 2) == [2, 4, 4, 8, 8] and make_model_input_shape(m, 1, T=6) == [1, 4, 6, 8, 8]
+    assert torch.equal(m.betas, SO.linear_sd_betas().to(torch.float32)) and m.num_timesteps == 1000
+    smp = DDIMSampler(m)
+    smp.make_schedule(50, ddim_eta=0.0)
+    ts, alphas, alphas_prev, sigmas = SO.ddim_schedule(torch.cumprod(1 - SO.linear_sd_betas(), 0), 50, 0.0)
+    assert (smp.ddim_timesteps == ts).all() and abs(float(smp.ddim_alphas[7]) - float(alphas[7])) < 1e-7
+    with pytest.raises(RuntimeError):
+        m.get_learned_conditioning(['text'])
