@@ -364,12 +364,41 @@ def gold_vae_encode(m):
                os.path.join(GOLD, 'vae_encode.pt'))
 
 
+def gold_vid2vid_encode():
+    """vid2vid entry noise of the three samplers (samplers_common.py:123-145): DDIMSampler.stochastic_encode
+    (ddim/sampler.py:270-283), UniPCSampler.unipc_encode (uni_pc/sampler.py:20-29), GaussianDiffusion.add_noise
+    (gaussian_sampler.py:87-91) -- reference outputs for tests/test_modules_cpu.py."""
+    ref_shim.load_samplers()
+    from samplers.ddim.gaussian_sampler import GaussianDiffusion
+    from samplers.ddim.sampler import DDIMSampler
+    from samplers.uni_pc.sampler import UniPCSampler
+    import samplers.uni_pc.sampler as ups
+    ups.UniPCSampler.register_buffer = lambda self, name, attr: setattr(self, name, attr)
+    betas = SO.linear_sd_betas()
+    model = _SchedModel(betas)
+    g = torch.Generator().manual_seed(3)
+    lat = torch.randn(1, 4, 5, 6, 7, generator=g)
+    noise = torch.randn(1, 4, 5, 6, 7, generator=g)
+    out = {'lat_noise_seed': 3, 'shape': (1, 4, 5, 6, 7)}
+    for strength, steps in ((0.6, 20), (0.25, 30), (1.0, 10)):
+        n = int(strength * steps)
+        rd = DDIMSampler(model, device=torch.device('cpu'))
+        rd.make_schedule(steps)
+        r1 = rd.stochastic_encode(lat, torch.tensor([n]), noise=noise) if n < steps else None
+        r2 = UniPCSampler(model).unipc_encode(lat, torch.device('cpu'), strength, steps, noise=noise)
+        rg = GaussianDiffusion(model, betas)
+        r3 = rg.add_noise(lat, noise, rg.get_time_steps(n, 1)[0])
+        out[f's{strength}_n{steps}'] = {'ddim': r1, 'unipc': r2, 'gauss': r3}
+    torch.save(out, os.path.join(GOLD, 'vid2vid_encode.pt'))
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     m = ref_shim.load_modelscope()
     gold_samplers()
     gold_vae(m)
     gold_vae_encode(m)
+    gold_vid2vid_encode()
     tiny = UO.UNetConfig(dim=64)
     keep = ['input_blocks.0.0', 'input_blocks.0.1', 'input_blocks.1.0', 'input_blocks.1.1', 'input_blocks.1.2',
             'input_blocks.3', 'input_blocks.4.0', 'input_blocks.11.0', 'middle_block.1', 'middle_block.3',

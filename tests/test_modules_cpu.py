@@ -118,3 +118,27 @@ def test_videocrafter_latent_diffusion_layout_and_schedule():
     assert (smp.ddim_timesteps == ts).all() and abs(float(smp.ddim_alphas[7]) - float(alphas[7])) < 1e-7
     with pytest.raises(RuntimeError):
         m.get_learned_conditioning(['text'])
+
+
+@pytest.mark.parametrize('strength,steps', [(0.6, 20), (0.25, 30), (1.0, 10)])
+def test_vid2vid_entry_noise_matches_reference_fixture(gold_dir, strength, steps):
+    """encode_latent's three back ends (samplers_common.py:123-145) are host-side torch arithmetic: checked on CPU against
+    the reference's outputs (tests/golden/vid2vid_encode.pt, written by oracle/make_golden.py)."""
+    import os
+    from t2v_b200 import samplers as M
+    gd = torch.load(os.path.join(gold_dir, 'vid2vid_encode.pt'))
+    g = torch.Generator().manual_seed(gd['lat_noise_seed'])
+    lat = torch.randn(gd['shape'], generator=g)
+    noise = torch.randn(gd['shape'], generator=g)
+    ref = gd[f's{strength}_n{steps}']
+    betas = linear_sd_betas()
+    net = UNetSD(dim=64)
+    net.register_schedule(given_betas=betas.numpy())
+    n = int(strength * steps)
+    if ref['ddim'] is not None:
+        md = M.DDIMSampler(net, device=torch.device('cpu'))
+        md.make_schedule(steps)
+        assert torch.allclose(md.stochastic_encode(lat, torch.tensor([n]), noise=noise), ref['ddim'], rtol=0, atol=1e-6)
+    assert torch.equal(M.UniPCSampler(net).unipc_encode(lat, torch.device('cpu'), strength, steps, noise=noise), ref['unipc'])
+    mg = M.GaussianDiffusion(net, betas)
+    assert torch.equal(mg.add_noise(lat, noise, mg.get_time_steps(n, 1)[0]), ref['gauss'])
