@@ -5,6 +5,7 @@ ModelScope 24 frames x 256x256, 50-step DDIM (UI-default scheduler "DDIM_Gaussia
     python bench.py --gpus 1 --steps K --warmup W                      # this repo (B200, libt2v_b200.so)
     torchrun --nproc-per-node N ... bench.py --gpus N ...              # one independent clip per GPU (sample-DP, weak)
     python bench.py --impl reference ...                               # the reference algorithm on the host cores
+    python bench.py --impl torch_gpu ...                               # the reference's GPU path (fp16 autocast + SDPA eager torch ops)
 
 A "step" is one whole clip: 50 scheduler steps (each = one batched cond+uncond UNet forward + fused CFG/DDIM update)
 followed by the VAE decode of all frames.  `value` has inputs resident in HBM; `e2e` goes through the public
@@ -34,7 +35,7 @@ def parse():
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=3, help='timed clips')
     ap.add_argument('--warmup', type=int, default=3, help='untimed warm-up clips (>= 3)')
-    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference', 'torch_gpu'])
     ap.add_argument('--frames', type=int, default=24)
     ap.add_argument('--height', type=int, default=256)
     ap.add_argument('--width', type=int, default=256)
@@ -42,6 +43,8 @@ def parse():
     ap.add_argument('--sampler', default='DDIM_Gaussian')
     ap.add_argument('--cfg-scale', type=float, default=17.0)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-gpu-baseline', action='store_true', help='skip the torch-eager GPU comparator leg of the N=1 run')
+    ap.add_argument('--cpu-frames', type=int, default=0, help='frames of the CPU sample (0 = the metric\'s F)')
     return ap.parse_args()
 
 
@@ -89,15 +92,16 @@ class ClockSampler(threading.Thread):
 # --------------------------------------------------------------------------------------------- reference / CPU arm
 def cpu_reference_sample(args, nsteps=1, threads=None):
     """The reference ALGORITHM (oracle/: CPU restatement pinned bit-exact against the reference's modules) on the host
-    cores: one DDIM step (cond + uncond UNetSD forward + update) on a 2-frame slice of the workload at the target
-    resolution plus the VAE decode of one frame, scaled to the metric:
-        frames/s = F_s / (denoise_steps * t_step + F_s * t_vae_frame)."""
+    cores, as BASELINE.md section 4.2 prescribes: ONE DDIM_Gaussian step (cond + uncond UNetSD forward + update, fp32 eager)
+    at the metric's own shape (F frames x H x W) plus the VAE decode of one frame, extrapolated with
+        frames/s = F_s / (denoise_steps * t_step + F_s * t_vae_frame)        (F_s = F unless --cpu-frames shrinks the sample).
+    Returns (fps, t_step, t_vae, threads, F_s, per-sample wall seconds)."""
     from oracle import unet_oracle as UO, vae_oracle as VO, samplers_oracle as SO
-    # torch's CPU kernels scale poorly past ~16 threads on these small tensors (measured: 128 threads on the GPU box's
-    # host were 50x SLOWER than 8 threads here), so the baseline uses min(cores, 16) threads and reports that number
+    # torch's CPU kernels scale poorly past ~16 threads on these tensors (measured in round 1: 128 threads on the GPU box's
+    # host were 50x SLOWER than 8 threads), so the baseline uses min(cores, 16) threads and reports that number
     threads = threads or min(os.cpu_count() or 1, 16)
     torch.set_num_threads(threads)
-    Fs, h, w = 2, args.height // 8, args.width // 8
+    Fs, h, w = (args.cpu_frames or args.frames), args.height // 8, args.width // 8
     cfg = UO.UNetConfig()
     W = UO.make_weights(UO.param_specs(cfg), seed=0)
     Wv = UO.make_weights(VO.decoder_param_specs(VO.VAEConfig()), seed=3)
@@ -129,27 +133,115 @@ def cpu_reference_sample(args, nsteps=1, threads=None):
     t_step = sorted(t[0] for t in times)[len(times) // 2]
     t_vae = sorted(t[1] for t in times)[len(times) // 2]
     fps = Fs / (args.denoise_steps * t_step + Fs * t_vae)
-    return fps, t_step, t_vae, threads, Fs
+    return fps, t_step, t_vae, threads, Fs, [a + b for a, b in times]
+
+
+CPU_FORMULA = 'frames/s = F_s / (denoise_steps * t_step + F_s * t_vae_frame)'
 
 
 def run_reference(args):
+    """`--impl reference`: a "step" here is ONE bounded sample of the workload -- one DDIM_Gaussian step at the metric's F
+    plus one VAE frame on the host cores (about half a minute) -- so K is capped at 3 timed + 1 warm-up sample to keep the
+    run within a few minutes; `steps` / `ms_per_step` report what actually ran, `value` is the extrapolated metric."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
     n = max(1, min(args.steps, 3))
+    w = 1 if args.warmup > 0 else 0
     t0 = time.perf_counter()
-    fps, t_step, t_vae, threads, Fs = cpu_reference_sample(args, nsteps=n)
+    if w:
+        cpu_reference_sample(args, nsteps=1)
+    fps, t_step, t_vae, threads, Fs, walls = cpu_reference_sample(args, nsteps=n)
     wall = time.perf_counter() - t0
-    sample = (f'{n} x [1 DDIM_Gaussian step (cond+uncond UNetSD forward, fp32 eager) on a {Fs}-frame {args.height}x{args.width} '
-              f'slice + 1 VAE frame], scaled to {args.denoise_steps} steps: t_step {t_step:.2f}s t_vae {t_vae:.2f}s')
-    line = {'impl': 'reference', 'metric': METRIC, 'value': fps, 'unit': 'frames/s', 'n_gpus': args.gpus, 'steps': args.steps,
-            'warmup': args.warmup, 'ms_per_step': 1000.0 * args.frames / fps, 'higher_is_better': True, 'scaling': 'weak',
+    sample = (f'{n} x [1 DDIM_Gaussian step (cond + uncond UNetSD forward, fp32 eager) at {Fs} frames x {args.height}x{args.width} '
+              f'+ 1 VAE frame], median t_step {t_step:.2f}s t_vae {t_vae:.2f}s, {threads} threads; {CPU_FORMULA}')
+    line = {'impl': 'reference', 'metric': METRIC, 'value': fps, 'unit': 'frames/s', 'n_gpus': args.gpus, 'steps': n,
+            'warmup': w, 'steps_requested': args.steps, 'warmup_requested': args.warmup,
+            'ms_per_step': 1000.0 * sum(walls) / len(walls), 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic (seeded random-init weights, random conditioning)',
             'config': {'workload': f'ModelScope UNetSD {args.frames}f x {args.height}x{args.width}, {args.denoise_steps}-step '
-                                   f'{args.sampler}, cfg {args.cfg_scale}, + VAE decode', 'note': 'bounded CPU sample, see cpu_baseline.sample'},
+                                   f'{args.sampler}, cfg {args.cfg_scale}, + VAE decode',
+                       'step': 'one bounded CPU sample (see cpu_baseline.sample); value is extrapolated to the whole clip',
+                       'F_s': Fs, 'threads': threads, 'formula': CPU_FORMULA, 'ms_per_clip_extrapolated': 1000.0 * args.frames / fps},
             'cpu_baseline': {'value': fps, 'unit': 'frames/s', 'cores': threads, 'kind': 'port', 'sample': sample},
             'e2e': {'value': fps, 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'wall_s': wall}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------- reference GPU comparator
+def torch_gpu_clip_fn(args, dev):
+    """The reference's own GPU path, SURVEY.md section 8d / BASELINE.md section 4.1 (the ">= 15x" denominator): the same torch
+    ops as the reference module tree (oracle/, pinned against the reference on CPU) with fp16 weights under
+    torch.autocast('cuda') (t2v_pipeline.py:271), attention through F.scaled_dot_product_attention (t2v_model.py:566-569, the
+    only backend reachable on sm_100), TWO sequential B = 1 forwards per step (gaussian_sampler.py:161-162), the reference
+    sampler arithmetic, and the per-frame VAE loop with a .cpu() per frame (t2v_pipeline.py:347-355).  /root/reference does
+    not exist on the GPU box, so the module tree itself cannot be timed there; its restatement issues the same library
+    kernels (cuDNN / cuBLAS / SDPA / elementwise).  Model movement and torch_gc() calls of the reference are left out (they
+    would only slow it down).  Returns fn(seed) -> list of decoded frames on the host."""
+    from oracle import unet_oracle as UO, vae_oracle as VO, samplers_oracle as SO
+    cfg = UO.UNetConfig()
+    W = {k: v.half().to(dev) for k, v in UO.make_weights(UO.param_specs(cfg), seed=0).items()}
+    Wv = {k: v.half().to(dev) for k, v in UO.make_weights(VO.decoder_param_specs(VO.VAEConfig()), seed=3).items()}
+    betas = SO.linear_sd_betas()
+    g = torch.Generator().manual_seed(2)
+    c = torch.randn(1, 77, 1024, generator=g).half().to(dev)
+    uc = torch.randn(1, 77, 1024, generator=g).half().to(dev)
+    F, h, w = args.frames, args.height // 8, args.width // 8
+    UO.ATTN_IMPL = 'sdpa'
+
+    def model(x, t, y):
+        return UO.unet_forward(W, cfg, x, t.to(dev), y)
+
+    def clip(seed):
+        x_T = torch.randn((1, 4, F, h, w), generator=torch.Generator().manual_seed(seed)).to(dev)    # samplers_common.py:118-119
+        with torch.no_grad(), torch.autocast('cuda', dtype=torch.float16):
+            if args.sampler == 'DDIM':
+                x0 = SO.ddim_sample(model, betas, x_T, args.denoise_steps, c, uc, args.cfg_scale)
+            else:
+                x0 = SO.ddim_gaussian_sample(model, betas, x_T, args.denoise_steps, c, uc, args.cfg_scale)
+            frames = []
+            for chunk in torch.chunk(x0, chunks=F, dim=2):                       # one frame per decode call + .cpu()
+                frames.append(VO.vae_decode(Wv, VO.VAEConfig(), (chunk / 0.18215)[:, :, 0]).cpu())
+        return frames
+    return clip
+
+
+def time_torch_gpu(args, dev, clips, warm_clips=1):
+    clip = torch_gpu_clip_fn(args, dev)
+    for i in range(warm_clips):
+        clip(900 + i)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(clips):
+        clip(123 + i)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / clips
+    return args.frames / (ms / 1000.0), ms
+
+
+TORCH_GPU_KIND = ('reference ops restated (oracle/) as eager torch on the same GPU: fp16 autocast + SDPA, two sequential B=1 forwards '
+                  'per step, reference sampler arithmetic, per-frame VAE decode + .cpu()')
+
+
+def run_torch_gpu(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    n = max(1, min(args.steps, 3))
+    fps, ms = time_torch_gpu(args, dev, n, warm_clips=1)
+    line = {'impl': 'torch_gpu', 'metric': METRIC, 'value': fps, 'unit': 'frames/s', 'n_gpus': 1, 'steps': n, 'warmup': 1,
+            'steps_requested': args.steps, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'f16 autocast', 'data': 'synthetic (seeded random-init weights, random conditioning)',
+            'config': {'workload': f'ModelScope UNetSD {args.frames}f x {args.height}x{args.width}, {args.denoise_steps}-step '
+                                   f'{args.sampler}, cfg {args.cfg_scale}, + per-frame VAE decode', 'kind': TORCH_GPU_KIND},
+            'e2e': {'value': fps, 'unit': 'frames/s', 'h2d_bytes_per_step': int(4 * args.frames * (args.height // 8) * (args.width // 8) * 4),
+                    'd2h_bytes_per_step': int(args.frames * args.height * args.width * 3 * 4)}}
     print(json.dumps(line), flush=True)
 
 
@@ -253,6 +345,8 @@ def run_b200(args):
         vae_flops = pipe.autoencoder.flops(F, h, w)
         clip_flops = S * unet_flops + vae_flops
         launches_clip = S * (unet.num_launches() + 3) + 120
+        # per GPU: a clip-rendering unit (one GPU, or a CFG pair) finishes one clip every ms / steps
+        whole_clip_tflops = clip_flops / (ms / args.steps * 1e-3) / 1e12 / (world / n_units)
         line = {
             'metric': METRIC, 'value': fps, 'unit': 'frames/s', 'n_gpus': world, 'steps': args.steps, 'warmup': W,
             'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
@@ -269,19 +363,31 @@ def run_b200(args):
                     'd2h_bytes_per_step': int(F * H * Wd * 3)},
             'gpu_launches': int(launches_clip * args.steps),
             'clocks': clk.summary(),
-            'achieved_tflops_whole_clip': clip_flops / (ms / args.steps * 1e-3) / 1e12,
             'roofline': {'bound': 'tensor', 'achieved': achieved, 'peak': pk['tflops_sustained'], 'unit': 'TFLOP/s',
                          'frac': achieved / pk['tflops_sustained'], 'traffic': recorded_traffic(), 'peak_source': pk['source'],
+                         'kernel_frac': achieved / pk['tflops_sustained'],
+                         'whole_clip_tflops': whole_clip_tflops, 'whole_clip_frac': whole_clip_tflops / pk['tflops_sustained'],
+                         'whole_clip_frac_of_burst': whole_clip_tflops / pk['tflops_burst'],
                          'kernel': 'gemm_tc_kernel (tcgen05 implicit GEMM), all launches of one B=2 forward, CUDA events per launch',
                          'gemm_share_of_forward': gemm['ms'] / prof['total_ms'] if prof['total_ms'] else None,
                          'forward_breakdown_ms': {k: round(v['ms'], 3) for k, v in prof.items() if isinstance(v, dict)}},
         }
+        if world == 1 and not args.no_gpu_baseline:
+            # the ">= 15x" denominator of BASELINE.json's north_star: the reference's fp16 PyTorch path on this same GPU
+            try:
+                gfps, gms = time_torch_gpu(args, dev, clips=1, warm_clips=1)
+                line['gpu_eager_baseline'] = {'value': gfps, 'unit': 'frames/s', 'ms_per_clip': gms, 'kind': TORCH_GPU_KIND,
+                                              'sample': '1 warm-up clip + 1 timed clip, CUDA events'}
+                line['vs_torch_gpu'] = {'e2e_ratio': fps_e2e / gfps, 'device_resident_ratio': fps / gfps}
+            except Exception as ex:
+                line['gpu_eager_baseline'] = {'value': None, 'error': str(ex)[:300]}
         if world == 1 and not args.no_cpu_baseline:
             try:
-                cfps, t_step, t_vae, threads, Fs = cpu_reference_sample(args, nsteps=1)
-                line['cpu_baseline'] = {'value': cfps, 'unit': 'frames/s', 'cores': threads, 'kind': 'port',
-                                        'sample': f'1 DDIM_Gaussian step (2 UNetSD forwards, fp32) on a {Fs}-frame {H}x{Wd} slice + 1 VAE '
-                                                  f'frame, scaled to {S} steps (t_step {t_step:.2f}s, t_vae {t_vae:.2f}s)'}
+                cfps, t_step, t_vae, threads, Fs, _ = cpu_reference_sample(args, nsteps=1)
+                line['cpu_baseline'] = {'value': cfps, 'unit': 'frames/s', 'cores': threads, 'kind': 'port', 'F_s': Fs,
+                                        'formula': CPU_FORMULA,
+                                        'sample': f'1 DDIM_Gaussian step (2 UNetSD forwards, fp32 eager) at {Fs} frames x {H}x{Wd} + 1 VAE '
+                                                  f'frame, extrapolated to {S} steps (t_step {t_step:.2f}s, t_vae {t_vae:.2f}s)'}
             except Exception as ex:                 # the baseline is informational; never lose the GPU number over it
                 line['cpu_baseline'] = {'value': None, 'error': str(ex)[:200]}
         print(json.dumps(line), flush=True)
@@ -293,6 +399,8 @@ def main():
     args = parse()
     if args.impl == 'reference':
         run_reference(args)
+    elif args.impl == 'torch_gpu':
+        run_torch_gpu(args)
     else:
         run_b200(args)
 

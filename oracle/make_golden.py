@@ -4,6 +4,7 @@ restatement against it while doing so.  Run in the build container (the referenc
 on the GPU box):
 
     python oracle/make_golden.py            # writes tests/golden/*.pt, prints oracle-vs-reference errors
+    python oracle/make_golden.py unet_cfg2  # only the named fixtures
 
 Fixtures hold inputs' seeds + reference OUTPUTS only; weights are regenerated from seeds by
 oracle.unet_oracle.make_weights (bit-identical on any host with the same torch build).
@@ -162,6 +163,130 @@ def gold_unet(m, name, cfg, F, h, w, wseed, keep_taps):
     return out
 
 
+
+def gold_unet_step(m, name, cfg, F, h, w, wseed, unipc=True):
+    """Full-size single-step gate at a BASELINE shape (config 2: 24 f x 32 x 32 latent): the reference module's eps for the
+    cond / uncond branch at the first timestep and the latent after ONE update of each scheduler, produced by the reference
+    sampler classes.  Reference forwards are memoised on (x, t, ctx) -- the first two model calls of DDIM_Gaussian and DDIM
+    are the eps_cond / eps_uncond forwards themselves -- so the fixture costs 2 (+4 for UniPC) reference forwards."""
+    torch.manual_seed(0)
+    net = build_ref_unet(m, cfg)
+    specs = UO.param_specs(cfg)
+    W = UO.make_weights(specs, seed=wseed)
+    net.load_state_dict(W, strict=True)
+    x, c, uc = synth_inputs(F, h, w, ctx_dim=cfg.context_dim)
+    memo = {}
+
+    def ref_forward(xx, tt, cc):
+        key = (float(tt.reshape(-1)[0]), float(cc.sum()), float(xx.double().sum()), float(xx.double().abs().sum()))
+        if key not in memo:
+            t0 = time.time()
+            with torch.no_grad():
+                memo[key] = net(xx, tt, cc)
+            print(f'[{name}] reference forward t={key[0]:.1f} {time.time() - t0:.1f}s', flush=True)
+        return memo[key]
+
+    t = torch.tensor([981])
+    eps_c = ref_forward(x, t, c)
+    eps_u = ref_forward(x, t, uc)
+    t0 = time.time()
+    o_c = UO.unet_forward(W, cfg, x, t, c)
+    err = (o_c - eps_c).abs().max().item()
+    print(f'[{name}] oracle forward {time.time() - t0:.1f}s; oracle-vs-reference max|d| = {err:.3e} '
+          f'(ref absmax {eps_c.abs().max().item():.3f})', flush=True)
+    assert err < 2e-4
+    out = {'cfg': cfg.__dict__, 'F': F, 'h': h, 'w': w, 'wseed': wseed, 'x_seed': 123, 'ctx_seed': 2, 't': 981,
+           'eps_cond': eps_c, 'eps_uncond': eps_u}
+    smp = ref_shim.load_samplers()
+    betas = SO.linear_sd_betas()
+    net.register_schedule(given_betas=betas.numpy())
+    smp.SamplerBase('x', None).register_buffers_to_model(net, betas, torch.device('cpu'))
+    from samplers.ddim.gaussian_sampler import GaussianDiffusion
+    from samplers.ddim.sampler import DDIMSampler
+    from samplers.uni_pc.sampler import UniPCSampler
+    import samplers.uni_pc.sampler as ups
+    ups.UniPCSampler.register_buffer = lambda self, nm, attr: setattr(self, nm, attr)
+
+    class _Stop(Exception):
+        pass
+
+    class Wrapped:
+        def __init__(self, stop_at):
+            self.calls, self.stop_at = [], stop_at
+            for a_ in ('device', 'betas', 'alphas_cumprod', 'alphas_cumprod_prev', 'num_timesteps', 'parameterization'):
+                setattr(self, a_, getattr(net, a_))
+
+        def __call__(self, xx, tt, cc):
+            self.calls.append(xx.clone())
+            if len(self.calls) == self.stop_at:
+                raise _Stop()
+            return ref_forward(xx, tt, cc)
+
+    def first_update(run, stop_at):
+        wm = Wrapped(stop_at)
+        try:
+            run(wm)
+        except _Stop:
+            pass
+        return wm.calls[-1]
+
+    S = 50
+    out['ddim_gaussian_x1'] = first_update(
+        lambda wm: GaussianDiffusion(wm, betas).sample(x_T=x, S=S, conditioning=c, unconditional_conditioning=uc,
+                                                       unconditional_guidance_scale=17.0, eta=0.0), 3)
+    out['ddim_x1'] = first_update(
+        lambda wm: DDIMSampler(wm, device=torch.device('cpu')).sample(
+            S=S, batch_size=1, shape=tuple(x.shape), conditioning=c, x_T=x, unconditional_guidance_scale=17.0,
+            unconditional_conditioning=uc, eta=0.0), 3)
+    if unipc:
+        out['unipc_x1'] = first_update(
+            lambda wm: UniPCSampler(wm).sample(S=30, batch_size=1, shape=tuple(x.shape), conditioning=c, x_T=x,
+                                               unconditional_guidance_scale=17.0, unconditional_conditioning=uc,
+                                               strength=None), 5)
+    # the oracle samplers fed with the REFERENCE eps (memoised) must produce the same updates: pins the schedulers at this shape
+    for key, stop_at, fn in (
+            ('ddim_gaussian_x1', 3, lambda om: SO.ddim_gaussian_sample(om, betas, x, S, c, uc, 17.0)),
+            ('ddim_x1', 3, lambda om: SO.ddim_sample(om, betas, x, S, c, uc, 17.0)),
+            ('unipc_x1', 5, lambda om: SO.unipc_sample(om, betas, x, 30, c, uc, 17.0))):
+        if key not in out:
+            continue
+        om = Wrapped(stop_at)
+        try:
+            fn(om)
+        except _Stop:
+            pass
+        d = (om.calls[-1] - out[key]).abs().max().item()
+        print(f'[{name}] {key}: oracle-sampler-vs-reference max|d| = {d:.3e}', flush=True)
+        assert d < 5e-4, (key, d)
+    torch.save(out, os.path.join(GOLD, name + '.pt'))
+    return out
+
+
+def gold_unet_forward_only(m, name, cfg, F, h, w, wseed, B=1):
+    """One reference forward (cond branch) at a shape that exercises a different kernel plan: config 3's S = 9216 spatial
+    sequences (2 frames of 72 x 128 latent), or a 125-frame temporal path on a narrow net (config 4)."""
+    torch.manual_seed(0)
+    net = build_ref_unet(m, cfg)
+    W = UO.make_weights(UO.param_specs(cfg), seed=wseed)
+    net.load_state_dict(W, strict=True)
+    x, c, uc = synth_inputs(F, h, w, ctx_dim=cfg.context_dim)
+    if B == 2:
+        x = torch.cat([x, x.flip(2) * 0.5], 0)
+        c = torch.cat([c, uc], 0)
+    t = torch.tensor([981, 37][:B])
+    t0 = time.time()
+    with torch.no_grad():
+        eps = net(x, t, c)
+    t1 = time.time()
+    o = UO.unet_forward(W, cfg, x, t, c)
+    err = (o - eps).abs().max().item()
+    print(f'[{name}] reference {t1 - t0:.1f}s oracle {time.time() - t1:.1f}s; oracle-vs-reference max|d| = {err:.3e} '
+          f'(ref absmax {eps.abs().max().item():.3f})', flush=True)
+    assert err < 2e-4
+    torch.save({'cfg': cfg.__dict__, 'F': F, 'h': h, 'w': w, 'B': B, 'wseed': wseed, 'x_seed': 123, 'ctx_seed': 2, 't': t,
+                'eps': eps.half() if eps.numel() > (1 << 20) else eps}, os.path.join(GOLD, name + '.pt'))
+
+
 class _SchedModel:
     """Stand-in denoiser exposing what the reference samplers read from the model
     (ddim/sampler.py:14,27-33; uni_pc/sampler.py:11-12; samplers_common.py:77-83)."""
@@ -278,7 +403,7 @@ def build_ref_vc_unet(cfg: VC.VCConfig):
                      use_relative_position=cfg.use_relative_position).eval()
 
 
-def gold_vc_unet(name, cfg: VC.VCConfig, B, T, h, w, L, wseed):
+def gold_vc_unet(name, cfg: VC.VCConfig, B, T, h, w, L, wseed, half_out=False):
     """VideoCrafter UNetModel: reference output on seeded inputs / weights; asserts the restatement."""
     torch.manual_seed(0)
     net = build_ref_vc_unet(cfg)
@@ -302,7 +427,7 @@ def gold_vc_unet(name, cfg: VC.VCConfig, B, T, h, w, L, wseed):
     print(f'[vc_unet:{name}] reference {t1 - t0:.1f}s; oracle-vs-reference max|d| = {err:.3e} '
           f'(ref absmax {ref.abs().max().item():.3f}), params {sum(v.numel() for v in W.values()) / 1e6:.2f} M')
     assert err <= 1e-5 * max(1.0, ref.abs().max().item())
-    torch.save({'wseed': wseed, 'x_seed': 123, 'ctx_seed': 2, 'shape': (B, 4, T, h, w), 'L': L, 't': t, 'out': ref,
+    torch.save({'wseed': wseed, 'x_seed': 123, 'ctx_seed': 2, 'shape': (B, 4, T, h, w), 'L': L, 't': t, 'out': ref.half() if half_out else ref,
                 'cfg': {'model_channels': cfg.model_channels, 'context_dim': cfg.context_dim,
                         'temporal_length': cfg.temporal_length}},
                os.path.join(GOLD, name + '.pt'))
@@ -392,25 +517,43 @@ def gold_vid2vid_encode():
     torch.save(out, os.path.join(GOLD, 'vid2vid_encode.pt'))
 
 
-def main():
+def main(only=None):
     os.makedirs(GOLD, exist_ok=True)
     m = ref_shim.load_modelscope()
-    gold_samplers()
-    gold_vae(m)
-    gold_vae_encode(m)
-    gold_vid2vid_encode()
+    want = lambda n: only is None or n in only      # noqa: E731
+    if want('samplers'):
+        gold_samplers()
+    if want('vae_decode'):
+        gold_vae(m)
+    if want('vae_encode'):
+        gold_vae_encode(m)
+    if want('vid2vid_encode'):
+        gold_vid2vid_encode()
     tiny = UO.UNetConfig(dim=64)
     keep = ['input_blocks.0.0', 'input_blocks.0.1', 'input_blocks.1.0', 'input_blocks.1.1', 'input_blocks.1.2',
             'input_blocks.3', 'input_blocks.4.0', 'input_blocks.11.0', 'middle_block.1', 'middle_block.3',
             'output_blocks.0.0', 'output_blocks.2.1', 'output_blocks.5.3', 'output_blocks.11.2']
-    gold_unet(m, 'unet_tiny', tiny, F=3, h=16, w=8, wseed=1, keep_taps=keep)
-    if os.environ.get('T2V_GOLD_FULL', '1') == '1':
+    if want('unet_tiny'):
+        gold_unet(m, 'unet_tiny', tiny, F=3, h=16, w=8, wseed=1, keep_taps=keep)
+    # 125 frames through the temporal conv / temporal attention / 5-D GroupNorm path on the narrow net (config 4's frame count)
+    if want('unet_f125'):
+        gold_unet_forward_only(m, 'unet_f125', tiny, F=125, h=8, w=8, wseed=1, B=2)
+    full = os.environ.get('T2V_GOLD_FULL', '1') == '1'
+    if full and want('unet_cfg1'):
         gold_unet(m, 'unet_cfg1', UO.UNetConfig(), F=4, h=16, w=16, wseed=0, keep_taps=[])
-    gold_vc_ddim()
-    gold_vc_unet('vc_unet_tiny', VC.VCConfig(model_channels=64, context_dim=48, temporal_length=4), B=2, T=4, h=8, w=8, L=7, wseed=3)
-    if os.environ.get('T2V_GOLD_FULL', '1') == '1':
+    if full and want('unet_cfg2'):       # the shape every bench number is quoted on: 24 frames x 256^2
+        gold_unet_step(m, 'unet_cfg2', UO.UNetConfig(), F=24, h=32, w=32, wseed=0)
+    if full and want('unet_cfg3_slice'):  # config 3's spatial sequence length S = 72 * 128 = 9216, 2 frames
+        gold_unet_forward_only(m, 'unet_cfg3_slice', UO.UNetConfig(), F=2, h=72, w=128, wseed=0)
+    if want('vc_ddim'):
+        gold_vc_ddim()
+    if want('vc_unet_tiny'):
+        gold_vc_unet('vc_unet_tiny', VC.VCConfig(model_channels=64, context_dim=48, temporal_length=4), B=2, T=4, h=8, w=8, L=7, wseed=3)
+    if full and want('vc_unet_full'):
         gold_vc_unet('vc_unet_full', VC.VCConfig(), B=1, T=16, h=16, w=16, L=77, wseed=0)
+    if full and want('vc_unet_cfg5'):     # config 5's per-GPU shape: 16 frames x 256^2
+        gold_vc_unet('vc_unet_cfg5', VC.VCConfig(), B=1, T=16, h=32, w=32, L=77, wseed=0, half_out=True)
 
 
 if __name__ == '__main__':
-    main()
+    main(set(sys.argv[1:]) or None)

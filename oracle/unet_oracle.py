@@ -187,6 +187,12 @@ def sinusoidal_embedding(t, dim):
     return e
 
 
+# Which branch of CrossAttention.forward (:556-582) is restated: 'math' = the einsum + softmax fallback (:570-580; the CPU
+# gate), 'sdpa' = F.scaled_dot_product_attention on (b h) n d tensors (:566-569; the only backend the reference can reach
+# on sm_100: xformers is capped at capability 9.0, :556).  bench.py's GPU comparator and the autocast parity tests set 'sdpa'.
+ATTN_IMPL = 'math'
+
+
 def _attention(W, p, x, ctx, heads):
     """CrossAttention.forward :540-584 (softmax(q k^T d^-1/2) v, then to_out)."""
     q = F.linear(x, W[p + '.to_q.weight'])
@@ -200,8 +206,12 @@ def _attention(W, p, x, ctx, heads):
         return t.reshape(t.shape[0], t.shape[1], heads, d).permute(0, 2, 1, 3)
 
     q, k, v = split(q), split(k), split(v)
-    sim = torch.matmul(q, k.transpose(-1, -2)) * (d ** -0.5)
-    o = torch.matmul(sim.softmax(dim=-1), v)
+    if ATTN_IMPL == 'sdpa':
+        o = F.scaled_dot_product_attention(q.reshape(-1, q.shape[2], d), k.reshape(-1, k.shape[2], d),
+                                           v.reshape(-1, v.shape[2], d), dropout_p=0.0).reshape(B, heads, N, d)
+    else:
+        sim = torch.matmul(q, k.transpose(-1, -2)) * (d ** -0.5)
+        o = torch.matmul(sim.softmax(dim=-1), v)
     o = o.permute(0, 2, 1, 3).reshape(B, N, C)
     return F.linear(o, W[p + '.to_out.0.weight'], W[p + '.to_out.0.bias'])
 

@@ -53,8 +53,17 @@ int ParamStore::set(const std::string& name, const void* src, int dtype, int ndi
         }
         cudaMemsetAsync(p.data, 0, ((p.elems + 7) / 8 * 8) * sizeof(__half), s);   // zero tail: padded bias reads
     }
-    int rc = convert_to_f16(src, dtype, p.data, p.elems, s);
-    if (rc != 0) return rc;
+    // fp16 sources (the normal case: the reference pipeline calls .half() on the model) are a plain device-to-device copy --
+    // no kernel launch per parameter, so a process's launch list starts with the packing / forward kernels
+    if (dtype == 0) {
+        if (cudaMemcpyAsync(p.data, src, p.elems * sizeof(__half), cudaMemcpyDeviceToDevice, s) != cudaSuccess) {
+            set_error("cudaMemcpyAsync failed for parameter '%s'", name.c_str());
+            return -5;
+        }
+    } else {
+        int rc = convert_to_f16(src, dtype, p.data, p.elems, s);
+        if (rc != 0) return rc;
+    }
     p.set = true;
     ++version_;
     invalidate_packed();

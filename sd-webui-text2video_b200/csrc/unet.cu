@@ -9,6 +9,7 @@
 #include "../../include/t2v_b200.h"
 #include "runtime.cuh"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
 #include <cstdio>
@@ -37,6 +38,7 @@ struct t2v_unet {
     std::vector<std::vector<Blk>> ins, outs;
     std::vector<Blk> mid;
     std::map<std::string, std::unique_ptr<Plan>> plans;      // key: "B,F,h,w,L"
+    std::vector<std::string> plan_lru;                       // most recently used last; bounded (T2V_MAX_PLANS, default 4)
     bool taps_enabled = false;
     int last_launches = 0;
     // fixed staging for graph replay
@@ -819,11 +821,42 @@ std::map<Plan*, IO> g_io;
 Plan* get_plan(t2v_unet* u, int B, int F, int h, int w, int L, cudaStream_t stream) {
     char key[96];
     snprintf(key, sizeof(key), "%d,%d,%d,%d,%d,%d", B, F, h, w, L, u->taps_enabled ? 1 : 0);
+    auto touch = [&](const std::string& k) {
+        auto& l = u->plan_lru;
+        l.erase(std::remove(l.begin(), l.end(), k), l.end());
+        l.push_back(k);
+    };
     auto it = u->plans.find(key);
-    if (it != u->plans.end() && it->second->weights_version == u->params.version()) return it->second.get();
+    if (it != u->plans.end() && it->second->weights_version == u->params.version()) {
+        touch(key);
+        return it->second.get();
+    }
     if (it != u->plans.end()) {
         g_io.erase(it->second.get());
         u->plans.erase(it);
+    }
+    {   // every plan owns an activation slab (GBs at video shapes) and an instantiated graph: keep only the most recently used
+        // few, and drop plans of an older weights version (they can never be replayed again)
+        static const int max_plans = getenv("T2V_MAX_PLANS") ? std::max(1, atoi(getenv("T2V_MAX_PLANS"))) : 4;
+        for (auto pit = u->plans.begin(); pit != u->plans.end();) {
+            if (pit->second->weights_version != u->params.version()) {
+                g_io.erase(pit->second.get());
+                u->plan_lru.erase(std::remove(u->plan_lru.begin(), u->plan_lru.end(), pit->first), u->plan_lru.end());
+                pit = u->plans.erase(pit);
+            } else {
+                ++pit;
+            }
+        }
+        while (static_cast<int>(u->plans.size()) >= max_plans && !u->plan_lru.empty()) {
+            const std::string victim = u->plan_lru.front();
+            u->plan_lru.erase(u->plan_lru.begin());
+            auto vit = u->plans.find(victim);
+            if (vit != u->plans.end()) {
+                cudaStreamSynchronize(stream);       // the victim's graph may still be in flight on this stream
+                g_io.erase(vit->second.get());
+                u->plans.erase(vit);
+            }
+        }
     }
     std::string miss;
     if (u->params.missing(&miss) > 0) {
@@ -844,6 +877,7 @@ Plan* get_plan(t2v_unet* u, int B, int F, int h, int w, int L, cudaStream_t stre
             cudaMemsetAsync(u->gn_ws, 0, need, stream);
             u->gn_ws_bytes = need;
             u->plans.clear();     // plans captured the old pointer
+            u->plan_lru.clear();
             g_io.clear();
         }
     }
@@ -867,6 +901,7 @@ Plan* get_plan(t2v_unet* u, int B, int F, int h, int w, int L, cudaStream_t stre
     Plan* raw = plan.get();
     g_io[raw] = io;
     u->plans[key] = std::move(plan);
+    touch(key);
     return raw;
 }
 

@@ -251,6 +251,11 @@ Plan* get_plan(t2v_vae* v, int frames, int h, int w, cudaStream_t stream) {
         g_vio.erase(it->second.get());
         v->plans.erase(it);
     }
+    if (v->plans.size() >= 3) {       // bounded cache: every plan owns a multi-GB activation slab (a webui session varies shapes)
+        cudaStreamSynchronize(stream);
+        for (auto& kv : v->plans) g_vio.erase(kv.second.get());
+        v->plans.clear();
+    }
     std::string miss;
     if (v->params.missing(&miss) > 0) {
         set_error("VAE parameters missing (e.g. '%s')", miss.c_str());
@@ -379,6 +384,11 @@ Plan* get_enc_plan(t2v_vae* v, int frames, int H, int W, cudaStream_t stream) {
     if (it != v->enc_plans.end()) {
         g_encio.erase(it->second.get());
         v->enc_plans.erase(it);
+    }
+    if (v->enc_plans.size() >= 3) {
+        cudaStreamSynchronize(stream);
+        for (auto& kv : v->enc_plans) g_encio.erase(kv.second.get());
+        v->enc_plans.clear();
     }
     std::string miss;
     if (v->enc_params.missing(&miss) > 0) {

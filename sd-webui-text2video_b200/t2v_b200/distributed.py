@@ -69,3 +69,35 @@ def exchange_eps(e_mine, group):
     out = [torch.empty_like(e_mine), torch.empty_like(e_mine)]
     dist.all_gather(out, e_mine, group=group)
     return out[0], out[1]
+
+
+def pair_shared(noise):
+    """Per-step sampler noise in CFG-split mode: both ranks of a pair must apply the IDENTICAL update, but each rank's global
+    CUDA generator is its own -- with eta > 0 the latents would silently drift apart after the first step.  Role 0's draw is
+    broadcast inside the pair (every rank still advances its own generator, so stream positions stay aligned)."""
+    if not cfg_split_enabled():
+        return noise
+    pair, role, grp = cfg_pair()
+    dist.broadcast(noise, src=2 * pair, group=grp)
+    return noise
+
+
+def pair_callback(callback, *args):
+    """Runs the per-step host callback; in CFG-split mode the decision to interrupt is made collective inside the pair (a
+    callback raising on one rank only would leave its partner blocked in the next eps all-gather)."""
+    if not cfg_split_enabled():
+        return callback(*args)
+    _, _, grp = cfg_pair()
+    err = None
+    try:
+        callback(*args)
+    except BaseException as e:            # InterruptedException derives from BaseException in the webui
+        err = e
+    flag = torch.tensor([1 if err is not None else 0], dtype=torch.int32,
+                        device='cuda' if dist.get_backend(grp) == 'nccl' else 'cpu')
+    dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=grp)
+    if err is not None:
+        raise err
+    if int(flag.item()) != 0:
+        from .samplers import InterruptedException
+        raise InterruptedException()

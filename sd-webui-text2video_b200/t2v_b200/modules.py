@@ -14,6 +14,7 @@ The leaf modules only HOLD parameters: the module tree is generated from the lib
 one C call.  There is no PyTorch fallback path.
 """
 import ctypes as C
+import weakref
 from functools import partial
 
 import numpy as np
@@ -115,8 +116,7 @@ class _NativeModule(nn.Module):
         fn = getattr(l, self._set_fn)
         stream = _lib.stream_ptr()
         for name, p in self.named_parameters():
-            key = (p.data_ptr(), p._version, p.dtype)
-            if self._shipped.get(name) == key:
+            if self._already_shipped(name, p):
                 continue
             if not p.is_cuda:
                 raise RuntimeError(f"parameter '{name}' is on {p.device}; move the model to the GPU "
@@ -128,8 +128,19 @@ class _NativeModule(nn.Module):
             shape = (C.c_int64 * t.dim())(*t.shape)
             rc = fn(self._handle, name.encode(), _lib.ptr(t), int(t.dtype == torch.float32), t.dim(), shape, stream)
             _lib.check(rc, f'{self._set_fn}({name})')
-            self._shipped[name] = key
+            self._mark_shipped(name, p)
         self._dirty = False
+
+    # A tensor counts as shipped only if it is the SAME Parameter object with the same storage / version / dtype.  The
+    # Stable-LoRA merger re-assigns `m.weight = nn.Parameter(new)` (stable_lora/scripts/lora_processor.py:236-242): a fresh
+    # Parameter starts at _version 0 and the caching allocator may hand it the block of the tensor shipped last time, so
+    # (data_ptr, _version, dtype) alone can collide; the weak reference pins object identity without keeping it alive.
+    def _already_shipped(self, name, p):
+        rec = self._shipped.get(name)
+        return rec is not None and rec[0] == (p.data_ptr(), p._version, p.dtype) and rec[1]() is p
+
+    def _mark_shipped(self, name, p):
+        self._shipped[name] = ((p.data_ptr(), p._version, p.dtype), weakref.ref(p))
 
 
 class UNetSD(_NativeModule):
@@ -422,8 +433,7 @@ class AutoencoderKL(_NativeModule):
         for name, p in self.named_parameters():
             if name not in self._native_names:
                 continue
-            key = (p.data_ptr(), p._version, p.dtype)
-            if self._shipped.get(name) == key:
+            if self._already_shipped(name, p):
                 continue
             if not p.is_cuda:
                 raise RuntimeError(f"parameter '{name}' is on {p.device}; move the VAE to the GPU")
@@ -432,7 +442,7 @@ class AutoencoderKL(_NativeModule):
             shape = (C.c_int64 * t.dim())(*t.shape)
             _lib.check(l.t2v_vae_set_param(self._handle, name.encode(), _lib.ptr(t), int(t.dtype == torch.float32),
                                            t.dim(), shape, stream), f'vae_set_param({name})')
-            self._shipped[name] = key
+            self._mark_shipped(name, p)
         self._dirty = False
 
     def init_from_ckpt(self, path):

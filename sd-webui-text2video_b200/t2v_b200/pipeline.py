@@ -112,6 +112,8 @@ class TextToVideoSynthesis(object):
         strength = None if (strength == 0.0 and not is_vid2vid) else strength
         if latents is not None:
             latents = latents.to(self.device)       # the reference's get_noise discards its `.to(device)` (samplers_common.py:106)
+            if 'half precision' in str(cpu_vae):    # t2v_pipeline.py:257: vid2vid latents (and the mask) are rounded to fp16, which
+                latents = latents.half()            # also rounds the scheduler's entry latent (`.to(dtype=latent.dtype)`)
         latents, noise, shape = self.diffusion.get_noise(1, 4, frames, height, width, seed=seed, latents=latents)
         self.diffusion.get_sampler(sampler, return_sampler=False)
         x0 = self.diffusion.sample_loop(steps=steps, strength=strength, eta=eta, conditioning=c,

@@ -164,14 +164,16 @@ class GaussianDiffusion(object):
             sig = eta * torch.sqrt(((1 - alp) / (1 - al)) * (1 - al / alp))
             direction = torch.sqrt(1 - alp - sig ** 2)
             nz_mask = 1.0 if tv != 0 else 0.0
-            noise = torch.randn_like(xt)                      # drawn every step, as the reference does (:279)
+            noise = _dist.pair_shared(torch.randn_like(xt))   # drawn every step, as the reference does (:279)
             xt = _step_kernel(xt, e_c, e_u, 1.0 if unguided else g, self.guided_channels(xt.shape[1]), 0,
                               (sr, srm1, torch.sqrt(alp), direction, nz_mask * sig), noise,
                               cfg_fp16=(e_c.dtype == torch.float16))
-            if hasattr(self, 'inpaint_masking') and mask is not None:
-                torch.randn_like(xt)                          # the reference's inpaint hook draws and discards (:285-291)
+            if hasattr(self, 'inpaint_masking'):
+                # the reference overwrites `mask` with t.ne(0)... (:281), so its inpaint hook runs -- and draws one more
+                # randn_like -- on EVERY step whenever the hook is attached, whether or not the caller passed a mask (:285-291)
+                torch.randn_like(xt)
             if callback is not None:
-                callback(step)
+                _dist.pair_callback(callback, step)
         return xt
 
 
@@ -202,7 +204,11 @@ class DDIMSampler(object):
     def stochastic_encode(self, x0, t, use_original_steps=False, noise=None):
         idx = int(torch.as_tensor(t).reshape(-1)[0])
         noise = torch.randn_like(x0) if noise is None else noise
-        return math.sqrt(float(self.ddim_alphas[idx])) * x0 + float(self.ddim_sqrt_one_minus_alphas[idx]) * noise
+        # the reference's coefficients are (b,1,1,1) fp32 TENSORS (ddim/sampler.py:274-283 over fp32 buffers), so an fp16
+        # latent (vid2vid under 'half precision', t2v_pipeline.py:257) is promoted and the sum is formed in fp32
+        a = torch.tensor(float(self.ddim_alphas[idx]), dtype=torch.float32).sqrt()
+        s1m = torch.tensor(float(self.ddim_sqrt_one_minus_alphas[idx]), dtype=torch.float32)
+        return float(a) * x0.float() + float(s1m) * noise.float()
 
     @torch.no_grad()
     def sample(self, S, batch_size=1, shape=None, conditioning=None, callback=None, eta=0.0, mask=None, x0=None,
@@ -238,12 +244,12 @@ class DDIMSampler(object):
                 e_c, e_u = _eval_pair(self.model, img, ts, c, uc)
             a_t, a_prev = _f32(self.ddim_alphas[index]), _f32(self.ddim_alphas_prev[index])
             sigma, s1m = _f32(self.ddim_sigmas[index]), _f32(self.ddim_sqrt_one_minus_alphas[index])
-            noise = torch.randn(img.shape, device=img.device)
+            noise = _dist.pair_shared(torch.randn(img.shape, device=img.device))
             img = _step_kernel(img, e_c, e_u, 1.0 if unguided else g, img.shape[1], 1,
                                (s1m, a_t.sqrt(), a_prev.sqrt(), (1.0 - a_prev - sigma ** 2).sqrt(), sigma * temperature),
                                noise, cfg_fp16=(e_c.dtype == torch.float16))
             if callback:
-                callback(i)
+                _dist.pair_callback(callback, i)
         return img
 
 
@@ -395,7 +401,7 @@ class UniPCSampler(object):
             m_list.append(m_x if m_x is not None else data_pred(x, ts[init_order]))
             t_list.append(ts[init_order])
             if callback is not None:
-                callback()
+                _dist.pair_callback(callback)
         for step in range(order, S + 1):
             k = min(order, S + 1 - step)
             x, m_x = update(x, m_list, t_list, ts[step], k, step != S)
@@ -404,7 +410,7 @@ class UniPCSampler(object):
             if step < S:
                 m_list[-1] = m_x if m_x is not None else data_pred(x, ts[step])
             if callback is not None:
-                callback()
+                _dist.pair_callback(callback)
         return x
 
 

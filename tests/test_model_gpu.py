@@ -4,10 +4,10 @@ Checker = the CPU oracle (oracle/, pinned bit-exact against the reference) and t
 tests/golden.  The oracle is evaluated in fp32 on the fp16-ROUNDED weights the GPU path holds, so what is measured
 is our kernels' arithmetic error, not the weight quantisation.
 
-Tolerances (stated, fp16 storage + fp32 accumulate through ~600 layers): relative RMS error of eps <= 1e-2 and
-max |err| <= 3e-2 * max|ref| vs the fp32 oracle; BASELINE.json's rtol 1e-3 / atol 1e-4 is what the kernel-level
-tests (test_ops_gpu.py) hold per op -- it cannot hold end-to-end against an fp32 reference for ANY fp16 path,
-including the reference's own CUDA path (SURVEY.md section 7 'hard parts')."""
+Tolerances (fp16 storage + fp32 accumulate through ~600 layers): relative RMS error of eps <= RMS_GATE and max |err| <=
+MAX_GATE * max|ref| vs the fp32 oracle / reference fixtures = the measured values x 1.5 (the gates at
+BASELINE's own shapes, with the reference's fp16-autocast path as the yardstick, are in test_parity_gpu.py).
+BASELINE.json's element-wise rtol 1e-3 / atol 1e-4 is what the kernel-level tests (test_ops_gpu.py) hold per op."""
 import os
 
 import pytest
@@ -16,7 +16,11 @@ import torch
 from oracle import unet_oracle as UO, vae_oracle as VO, samplers_oracle as SO
 from oracle.make_golden import synth_inputs, analytic_model, _SchedModel
 
+from parity_util import report  # noqa: E402
+
 pytestmark = pytest.mark.gpu
+
+RMS_GATE, MAX_GATE = 4e-3, 1.6e-2
 
 
 def errs(a, b):
@@ -44,15 +48,15 @@ def test_tiny_unet_vs_reference_fixture_and_taps(tiny, gold_dir):
     net.enable_taps(True)
     out = net(x.cuda(), torch.tensor([g['t']]).cuda(), c.cuda())
     e = errs(out, g['eps_cond'])
-    assert e[1] < 1e-2 and e[0] < 3e-2, e
+    assert e[1] < RMS_GATE and e[0] < MAX_GATE, e
     for k, v in g.items():
         if k.startswith('tap:'):
             et = errs(net.read_tap(k[4:], tuple(v.shape)), v)
-            assert et[1] < 1e-2, (k, et)
+            assert et[1] < RMS_GATE, (k, et)
     net.enable_taps(False)
     out2 = net(x.cuda(), torch.tensor([g['t']]).cuda(), c.cuda())       # arena with buffer reuse
     assert torch.equal(out, out2)
-    assert errs(net(x.cuda(), torch.tensor([g['t']]).cuda(), uc.cuda()), g['eps_uncond'])[1] < 1e-2
+    assert errs(net(x.cuda(), torch.tensor([g['t']]).cuda(), uc.cuda()), g['eps_uncond'])[1] < RMS_GATE
 
 
 @pytest.mark.parametrize('B,Fr,h,w', [(2, 4, 8, 8), (1, 5, 8, 24), (1, 1, 8, 8), (3, 2, 16, 8)])
@@ -65,7 +69,7 @@ def test_tiny_unet_shapes_vs_oracle(tiny, B, Fr, h, w):
     ref = UO.unet_forward(Wh, cfg, x, t, y)
     out = net(x.cuda(), t.cuda(), y.cuda())
     e = errs(out, ref)
-    assert e[1] < 1e-2 and e[0] < 3e-2, e
+    assert e[1] < RMS_GATE and e[0] < MAX_GATE, e
     # batched CFG pair == two single forwards (samples are independent: per-sample 5-D GroupNorm / temporal attention)
     if B >= 2:
         single = net(x[:1].cuda(), t[:1].cuda(), y[:1].cuda())
@@ -79,7 +83,7 @@ def test_float_timesteps_and_longer_context(tiny):
     y = torch.randn(1, 154, 1024, generator=g).half().float()         # two 77-token prompt chunks
     t = torch.tensor([437.25])                                          # UniPC passes float times
     ref = UO.unet_forward(Wh, cfg, x, t, y)
-    assert errs(net(x.cuda(), t.cuda(), y.cuda()), ref)[1] < 1e-2
+    assert errs(net(x.cuda(), t.cuda(), y.cuda()), ref)[1] < RMS_GATE
 
 
 def test_weight_update_is_picked_up(tiny):
@@ -116,6 +120,7 @@ def test_vae_decode_vs_reference_fixture(gold_dir):
     z = torch.randn(g['z_shape'], generator=torch.Generator('cpu').manual_seed(g['z_seed'])) * g['z_scale']
     out = vae.decode(z.cuda())
     e = errs(out, g['out'])
+    report('vae_decode', max=e[0], rms=e[1])
     assert e[1] < 5e-3 and e[0] < 2e-2, e
     # batched video path + fused uint8 conversion == tensor2vid on the float output
     z5 = (z * 0.18215).view(1, 2, 4, 8, 16).permute(0, 2, 1, 3, 4).contiguous()
@@ -151,6 +156,31 @@ def test_samplers_vs_reference_trajectories(gold_dir, name, key, S, scale):
                      shape=tuple(x.shape), eta=0.0, batch_size=1, callback=lambda *a: calls.append(a))
     assert len(calls) == S
     assert torch.allclose(out.cpu(), g[key], rtol=0, atol=2e-4), (out.cpu() - g[key]).abs().max()
+
+
+def test_ddim_gaussian_eta_consumes_the_rng_like_the_reference():
+    """eta > 0: the reference draws randn_like(xt) for the step noise AND once more in its inpaint hook on every step
+    (gaussian_sampler.py:279,:285-291 -- `mask` is overwritten with t.ne(0) at :281, so the hook always runs once attached).
+    The oracle restates that; run on the same CUDA generator state the product sampler must give the same latent."""
+    from t2v_b200 import samplers
+    betas = SO.linear_sd_betas()
+
+    class M(_SchedModel):
+        def __call__(self, x, t, c):
+            return analytic_model(x, t.to(x.device), c)
+    model = M(betas)
+    model.device = torch.device('cuda')
+    x = torch.randn((1, 4, 5, 6, 7), generator=torch.Generator('cpu').manual_seed(5)).cuda()
+    c = torch.full((1, 77, 8), 0.25).cuda()
+    uc = torch.full((1, 77, 8), -0.5).cuda()
+    smp = samplers.Txt2VideoSampler(model, torch.device('cuda'), betas=betas, sampler_name='DDIM_Gaussian').sampler
+    assert hasattr(smp, 'inpaint_masking')
+    torch.manual_seed(11)
+    out = smp.sample(S=10, conditioning=c, unconditional_conditioning=uc, unconditional_guidance_scale=3.0, x_T=x,
+                     shape=tuple(x.shape), eta=0.7, batch_size=1, mask=None)
+    torch.manual_seed(11)
+    ref = SO.ddim_gaussian_sample(model, betas, x, 10, c, uc, 3.0, eta=0.7)
+    assert torch.allclose(out, ref, rtol=0, atol=2e-4), (out - ref).abs().max()
 
 
 def test_gaussian_cfg_quirk_and_fp16_rounding():
@@ -199,7 +229,8 @@ def test_vc_unet_vs_reference_fixture(gold_dir, name):
     ctx = torch.randn((B, g['L'], cfg.context_dim), generator=torch.Generator('cpu').manual_seed(g['ctx_seed']))
     out = net(x.cuda(), g['t'].cuda(), context=ctx.cuda())
     e = errs(out, g['out'])
-    assert e[1] < 1e-2 and e[0] < 3e-2, e
+    report('vc:' + name, max=e[0], rms=e[1])
+    assert e[1] < RMS_GATE and e[0] < MAX_GATE, e
     assert torch.equal(out, net(x.cuda(), g['t'].cuda(), context=ctx.cuda()))      # graph replay, bit-reproducible
 
 
@@ -215,7 +246,7 @@ def test_vc_unet_shapes_vs_oracle(B, T, h, w):
     t = torch.randint(0, 1000, (B,), generator=g)
     ref = VC.vc_unet_forward(Wh, cfg, x, t, ctx)
     e = errs(net(x.cuda(), t.cuda(), context=ctx.cuda()), ref)
-    assert e[1] < 1e-2 and e[0] < 3e-2, e
+    assert e[1] < RMS_GATE and e[0] < MAX_GATE, e
 
 
 # ---------------------------------------------------------------------------------------- full-size regressions
@@ -231,8 +262,8 @@ def test_full_modelscope_unet_vs_reference_fixture(gold_dir):
     x, c, uc = synth_inputs(g['F'], g['h'], g['w'])
     t = torch.tensor([g['t']]).cuda()
     e = errs(net(x.cuda(), t, c.cuda()), g['eps_cond'])
-    assert e[1] < 1e-2 and e[0] < 3e-2, e
-    assert errs(net(x.cuda(), t, uc.cuda()), g['eps_uncond'])[1] < 1e-2
+    assert e[1] < RMS_GATE and e[0] < MAX_GATE, e
+    assert errs(net(x.cuda(), t, uc.cuda()), g['eps_uncond'])[1] < RMS_GATE
 
 
 def test_activation_arena_reuse_does_not_change_results(monkeypatch):
@@ -276,7 +307,8 @@ def test_vae_encode_vs_reference_fixture_and_compute_latents(gold_dir):
     x = torch.rand(g['x_shape'], generator=torch.Generator('cpu').manual_seed(g['x_seed'])) * 2 - 1
     post = ae.encode(x.cuda())
     e = errs(post.mean, g['mean'])
-    assert e[1] < 1e-2 and e[0] < 3e-2, e
+    report('vae_encode_mean', max=e[0], rms=e[1])
+    assert e[1] < RMS_GATE and e[0] < MAX_GATE, e
     assert errs(post.logvar, g['logvar'])[1] < 2e-2
     assert post.sample(torch.zeros_like(post.mean)).equal(post.mode())
     # frames with odd tile counts + fp32 input, vs the oracle on the fp16-rounded weights

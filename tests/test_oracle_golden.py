@@ -144,3 +144,42 @@ def test_vae_encode_matches_reference_fixture(gold_dir):
     mom = VO.vae_encode_moments(W, cfg, x)
     assert torch.allclose(mom[:, :4], g['mean'], rtol=0, atol=1e-5)
     assert torch.allclose(torch.clamp(mom[:, 4:], -30.0, 20.0), g['logvar'], rtol=0, atol=1e-5)
+
+
+def test_unet_125_frames_matches_reference_fixture(gold_dir):
+    """Config 4's frame count through the temporal modules (narrow net, B = 2): oracle vs the reference output."""
+    g = torch.load(os.path.join(gold_dir, 'unet_f125.pt'))
+    cfg = UO.UNetConfig(dim=64)
+    W = UO.make_weights(UO.param_specs(cfg), seed=g['wseed'])
+    x, c, uc = synth_inputs(g['F'], g['h'], g['w'])
+    x = torch.cat([x, x.flip(2) * 0.5], 0)
+    out = UO.unet_forward(W, cfg, x, g['t'], torch.cat([c, uc], 0))
+    assert torch.allclose(out, g['eps'].float(), rtol=0, atol=2e-5)
+
+
+def test_full_size_fixtures_are_consistent(gold_dir):
+    """The full-model fixtures at BASELINE's shapes (config 2 / 3 / 5) are too expensive to re-derive in the CPU suite
+    (make_golden.py asserted oracle == reference when it wrote them); check their shapes and that the single-step latents
+    follow from the stored eps through the pinned scheduler restatement (DDIM_Gaussian: no model call needed)."""
+    g = torch.load(os.path.join(gold_dir, 'unet_cfg2.pt'))
+    assert (g['F'], g['h'], g['w']) == (24, 32, 32) and g['eps_cond'].shape == (1, 4, 24, 32, 32)
+    x, c, uc = synth_inputs(24, 32, 32)
+    calls = []
+
+    def model(xx, tt, cc):
+        calls.append(1)
+        if len(calls) > 2:
+            raise StopIteration
+        return g['eps_cond'] if len(calls) == 1 else g['eps_uncond']
+    tr = []
+    try:
+        SO.ddim_gaussian_sample(model, SO.linear_sd_betas(), x, 50, c, uc, 17.0, trace=tr)
+    except StopIteration:
+        pass
+    assert torch.allclose(tr[0], g['ddim_gaussian_x1'], rtol=0, atol=1e-6)
+    for k in ('ddim_x1', 'unipc_x1'):
+        assert g[k].shape == x.shape and torch.isfinite(g[k]).all()
+    g3 = torch.load(os.path.join(gold_dir, 'unet_cfg3_slice.pt'))
+    assert g3['eps'].shape == (1, 4, 2, 72, 128)
+    g5 = torch.load(os.path.join(gold_dir, 'vc_unet_cfg5.pt'))
+    assert tuple(g5['out'].shape) == (1, 4, 16, 32, 32)

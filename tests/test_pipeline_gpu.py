@@ -7,6 +7,8 @@ import torch
 
 from oracle import unet_oracle as UO, vae_oracle as VO, samplers_oracle as SO
 
+from parity_util import report  # noqa: E402
+
 pytestmark = pytest.mark.gpu
 
 TINY = {'unet_dim': 64}
@@ -55,6 +57,7 @@ def test_short_trajectory_and_decode_vs_oracle(pipe):
     ref = SO.ddim_gaussian_sample(lambda a, b, d: UO.unet_forward(Wh, cfg, a, b, d), SO.linear_sd_betas(), x_T, S,
                                   c.float(), uc.float(), 5.0)
     err = (latent.cpu() - ref).abs().max() / ref.abs().max()
+    report('pipeline:ddim_gaussian_4steps_tiny', max=float(err))
     assert err < 3e-2, err                      # 4 steps x 2 fp16 forwards each, vs fp32 oracle
     dec = VO.vae_decode({k: v.half().float() for k, v in Wv.items()}, VO.VAEConfig(),
                         (ref[0].permute(1, 0, 2, 3) / 0.18215))

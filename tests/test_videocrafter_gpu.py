@@ -7,6 +7,8 @@ import torch
 
 from oracle import unet_oracle as UO, vae_oracle as VO, vc_oracle as VC, samplers_oracle as SO
 
+from parity_util import report  # noqa: E402
+
 pytestmark = pytest.mark.gpu
 
 CFG = VC.VCConfig(model_channels=64, context_dim=48, temporal_length=4)
@@ -50,6 +52,7 @@ def test_ddim_trajectory_vs_oracle(ldm, S, scale, eta):
     ref = VC.vc_ddim_sample(lambda a, b, d: VC.vc_unet_forward(Wh, CFG, a, b, d), SO.linear_sd_betas(), x_T, S, c, uc, scale,
                             eta=eta, noise_gen=torch.Generator('cpu').manual_seed(11))
     err = (out.cpu() - ref).abs().max() / ref.abs().max()
+    report(f'vc_ddim_tiny:S{S}_g{scale}_eta{eta}', max=float(err))
     assert err < 3e-2, err
     assert 'x_inter' in inter
 
