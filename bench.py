@@ -42,6 +42,9 @@ def parse():
     ap.add_argument('--denoise-steps', type=int, default=50)
     ap.add_argument('--sampler', default='DDIM_Gaussian')
     ap.add_argument('--cfg-scale', type=float, default=17.0)
+    ap.add_argument('--mode', default='sample_dp', choices=['sample_dp', 'frame_shard'],
+                    help='N>1: sample_dp = one clip per GPU (weak scaling, the default the driver runs); frame_shard = ONE clip '
+                         'split over the N GPUs by frames (strong scaling, BASELINE config 4: --frames 125)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-gpu-baseline', action='store_true', help='skip the torch-eager GPU comparator leg of the N=1 run')
     ap.add_argument('--cpu-frames', type=int, default=0, help='frames of the CPU sample (0 = the metric\'s F)')
@@ -273,6 +276,8 @@ def run_b200(args):
     pipe = TextToVideoSynthesis(None, device=dev)
     randomize_(pipe.sd_model, seed=0)
     randomize_(pipe.autoencoder, seed=3)
+    frame_shard = args.mode == 'frame_shard' and world > 1
+    fs = pipe.enable_frame_shard() if frame_shard else None
     F, H, Wd = args.frames, args.height, args.width
     h, w = H // 8, Wd // 8
     S = args.denoise_steps
@@ -286,6 +291,15 @@ def run_b200(args):
         """inputs resident in HBM; result (uint8 frames) stays on the device"""
         x_T = torch.randn((1, 4, F, h, w), device=dev, generator=torch.Generator(device=dev).manual_seed(seed))
         smp = entry.init_sampler(pipe.sd_model, betas=pipe.diffusion.betas, device=dev)
+        if fs is not None:          # ONE clip over all ranks: this rank's frames through the loop, one latent all-gather, sharded VAE
+            fs.begin(F, seed)
+            try:
+                x_l = fs.local(x_T)
+                x0 = smp.sample(S=S, conditioning=c_dev, unconditional_conditioning=uc_dev,
+                                unconditional_guidance_scale=args.cfg_scale, x_T=x_l, shape=tuple(x_l.shape), eta=0.0, batch_size=1)
+            finally:
+                fs.end()
+            return fs.decode(fs.gather_latent(x0), 1.0 / SCALE_FACTOR)
         x0 = smp.sample(S=S, conditioning=c_dev, unconditional_conditioning=uc_dev, unconditional_guidance_scale=args.cfg_scale,
                         x_T=x_T, shape=tuple(x_T.shape), eta=0.0, batch_size=1)
         return pipe.autoencoder.decode_video(x0, 1.0 / SCALE_FACTOR, as_uint8=True)
@@ -297,7 +311,7 @@ def run_b200(args):
         return frames
 
     def gather(frames_u8):
-        if world > 1:     # the reference's gather_data: one all-gather of the decoded clips (lvdm/utils/dist_utils.py:14-19)
+        if world > 1 and fs is None:     # the reference's gather_data: one all-gather of the decoded clips (lvdm/utils/dist_utils.py:14-19)
             out = [torch.empty_like(frames_u8) for _ in range(world)]
             dist.all_gather(out, frames_u8)
 
@@ -321,6 +335,8 @@ def run_b200(args):
 
     from t2v_b200 import distributed as D
     unit, n_units = D.units()       # clip-rendering units: ranks (sample-DP) or rank pairs (T2V_CFG_SPLIT=1, distributed.py)
+    if fs is not None:
+        unit, n_units = 0, 1        # every rank works on the same clip (same seed)
     W = max(args.warmup, 1)
     for i in range(W):
         clip_device(1000 + i)
@@ -338,10 +354,10 @@ def run_b200(args):
     if rank == 0:
         pk = peaks()
         unet = pipe.sd_model
-        prof = unet.profile(2, F, h, w, 77)
+        prof = unet.profile(2, F, h, w, 77) if fs is None else {'gemm': {'ms': 0.0, 'flop': 0.0, 'launches': 0}, 'total_ms': 0.0}
         gemm = prof['gemm']
         achieved = gemm['flop'] / (gemm['ms'] * 1e-3) / 1e12 if gemm['ms'] > 0 else 0.0
-        unet_flops = unet.flops(2, F, h, w, 77)
+        unet_flops = unet.flops(2, F, h, w, 77) * (world if fs is not None else 1)     # sharded: flops() is this rank's share
         vae_flops = pipe.autoencoder.flops(F, h, w)
         clip_flops = S * unet_flops + vae_flops
         launches_clip = S * (unet.num_launches() + 3) + 120
@@ -349,12 +365,15 @@ def run_b200(args):
         whole_clip_tflops = clip_flops / (ms / args.steps * 1e-3) / 1e12 / (world / n_units)
         line = {
             'metric': METRIC, 'value': fps, 'unit': 'frames/s', 'n_gpus': world, 'steps': args.steps, 'warmup': W,
-            'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'strong' if fs is not None else 'weak', 'vs_baseline': None,
             'dtype': 'f16 (fp32 accumulate / norms / softmax)', 'data': 'synthetic (seeded random-init weights of the public '
             'ModelScope architecture, random CLIP-like conditioning)',
             'config': {'workload': f'ModelScope UNetSD {F}f x {H}x{Wd}, {S}-step {args.sampler}, cfg {args.cfg_scale}, batched '
                                    f'cond+uncond forward, + AutoencoderKL decode of {F} frames',
-                       'parallelism': (f'sample-DP x{world} (one clip per GPU, one NCCL all-gather of the decoded clips)' if n_units == world else
+                       'parallelism': (f'frame-shard x{world}: ONE clip, {F} frames split over the GPUs; activations exchanged inside the UNet '
+                                       f'kernels over NVLink peer memory ({unet.num_exchanges(F)} layout exchanges per forward, no NCCL call per '
+                                       'step), one NCCL all-gather of the final latent before a frame-sharded VAE' if fs is not None else
+                                       f'sample-DP x{world} (one clip per GPU, one NCCL all-gather of the decoded clips)' if n_units == world else
                                        f'CFG-pair split: {n_units} pair(s) of GPUs, cond / uncond branch per GPU, one eps all-gather per step'),
                        'l2': 'inputs larger than L2: 2.8 GB of fp16 weights are re-read every forward, activations stream through a '
                              'multi-GB arena', 'flop_per_clip': clip_flops},

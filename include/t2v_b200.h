@@ -84,6 +84,38 @@ int t2v_unet_profile(t2v_unet* u, int B, int F, int h, int w, int L, void* strea
 long long t2v_unet_read_tap(t2v_unet* u, const char* name, void* dst, long long cap_elems, void* stream);
 int t2v_unet_enable_taps(t2v_unet* u, int on);
 
+/* ------------------------------------------------------------------------------------------ frame-sharded clip
+ * ONE clip split over the GPUs of a node, one process per GPU (BASELINE config 4: 125 frames over 8 x B200).  Frames are
+ * independent inside the spatial modules and coupled in TemporalConvBlock_v2 (t2v_model.py:1201-1212), TemporalTransformer
+ * (:724, :734-738) and every 5-D GroupNorm; the library keeps activations frame-sharded in the spatial modules, transposes
+ * them to a pixel-sharded layout around each temporal module with a kernel that writes straight into the peers' buffers
+ * over NVLink (CUDA IPC mappings), and sums the 5-D GroupNorm statistics across ranks inside the statistics kernel.  No
+ * NCCL call and no host synchronisation happens inside a forward; the caller's only collective is the exchange of the
+ * fixed-size exports below (any byte all-gather: torch.distributed in the Python mirror) once per shape.
+ *   1. t2v_unet_shard_setup(u, rank, nranks)                    every rank, once
+ *   2. t2v_unet_shard_prepare(u, shape..., &mine)               builds this rank's plan, fills `mine`
+ *   3. all-gather the exports in rank order -> all[nranks]
+ *   4. t2v_unet_shard_connect(u, shape..., all)                 maps the peers' slabs
+ *   5. t2v_unet_forward(u, x_local, ..., F = TOTAL frames ...)  x / out hold this rank's frames [B, C, F_local, h, w];
+ *      every rank must issue the same sequence of forwards (the exchange kernels wait for their peers).              */
+typedef struct {
+    unsigned char comm_handle[64];        /* cudaIpcMemHandle_t of the rank's flag / GroupNorm exchange region */
+    unsigned char slab_handle[64];        /* cudaIpcMemHandle_t of the plan's activation slab */
+    int rank, nranks;
+    int n_exchanges, n_groupnorms;
+    long long dst_offset[192];            /* byte offset of every exchange's destination buffer inside the slab */
+} t2v_shard_export;
+int t2v_unet_shard_setup(t2v_unet* u, int rank, int nranks);
+int t2v_unet_shard_prepare(t2v_unet* u, int B, int F, int h, int w, int L, void* stream, t2v_shard_export* out);
+int t2v_unet_shard_connect(t2v_unet* u, int B, int F, int h, int w, int L, const t2v_shard_export* all, void* stream);
+/* 1 if the plan of this shape exists for the current weights and is connected (a re-shipped parameter or a plan-cache
+ * eviction drops the plan: prepare + connect again -- every rank takes the same decision, the inputs are identical) */
+int t2v_unet_shard_connected(t2v_unet* u, int B, int F, int h, int w, int L);
+/* device-side barrier over the ranks (after connect; all ranks must call it) */
+int t2v_unet_shard_barrier(t2v_unet* u, void* stream);
+/* this rank's frame range [begin, end) of an F-frame clip and the exchange count of the last forward */
+int t2v_unet_shard_info(t2v_unet* u, int F, int* frame_begin, int* frame_end, int* n_exchanges);
+
 /* ------------------------------------------------------------------------------------------ VAE decoder
  * replaces AutoencoderKL.decode (modelscope/t2v_model.py:1646-1649) + ldm Decoder (vendored twin
  * videocrafter/lvdm/models/modules/autoencoder_modules.py:484-596) and the per-frame loop of

@@ -8,11 +8,14 @@
 
 namespace t2v {
 
+struct GnShard;      // shard.cuh: cross-rank part of a 5-D GroupNorm of a frame-sharded clip
+
 // ---------------------------------------------------------------- norm.cu
 size_t gn_workspace_bytes(int rows_per_inst, int n_inst, int num_sms);
 int groupnorm_silu(const __half* x, long long ldx, __half* y, long long ldy, long long rows, int C, int rows_per_inst,
                    const __half* gamma, const __half* beta, float eps, int silu, void* workspace, int num_sms,
-                   cudaStream_t stream, int phase = 0);   // phase 0: stats + apply, 1: stats only, 2: apply only
+                   cudaStream_t stream, int phase = 0,    // phase 0: stats + apply, 1: stats only, 2: apply only
+                   const GnShard* shard = nullptr);       // non-null: statistics are summed over the ranks of a sharded clip
 int layernorm(const __half* x, long long ldx, __half* y, long long ldy, long long rows, int C, const __half* gamma,
               const __half* beta, float eps, cudaStream_t stream);
 

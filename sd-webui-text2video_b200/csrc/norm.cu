@@ -6,9 +6,11 @@
 // fp32 math throughout (the reference runs group_norm / layer_norm / SiLU-after-norm in fp32 under autocast and
 // rounds to fp16 only when the value enters the next conv/linear -- exactly where these kernels round).
 #include <algorithm>
+#include <cstring>
 
 #include "common.cuh"
 #include "kernels.cuh"
+#include "shard.cuh"
 
 namespace t2v {
 
@@ -41,7 +43,7 @@ __global__ void __launch_bounds__(kNormThreads) gn_stats_kernel(const __half* __
                                                                 int rows_per_inst, int rows_per_chunk, int nchunks,
                                                                 float eps, float2* __restrict__ partial,
                                                                 unsigned int* __restrict__ counters,
-                                                                float2* __restrict__ stats) {
+                                                                float2* __restrict__ stats, const GnShard gs) {
     griddep_wait();
     griddep_launch_small();
     extern __shared__ float sm[];          // red[2][RL][C] | s_sum[C] | s_sq[C]
@@ -155,7 +157,31 @@ __global__ void __launch_bounds__(kNormThreads) gn_stats_kernel(const __half* __
                 a += fold[part][threadIdx.x][0];
                 b += fold[part][threadIdx.x][1];
             }
-            const double n = static_cast<double>(rows_per_inst) * cpg;
+            double n = static_cast<double>(rows_per_inst) * cpg;
+            if (gs.peers.nranks > 1) {
+                // 5-D GroupNorm of a frame-sharded clip (pixel-sharded layout): this rank's (sum, sumsq) of the sample go to
+                // every rank over NVLink peer stores; all ranks then fold the P contributions in rank order, so mean / rstd
+                // are bit-identical everywhere.  threadIdx.x < 32 = warp 0 only.
+                const int me = gs.peers.rank, nr = gs.peers.nranks;
+                ShardComm* mine = gs.peers.comm[me];
+                const unsigned int e = *reinterpret_cast<volatile unsigned int*>(&mine->epoch);
+                for (int r = 0; r < nr; ++r) gs.peers.comm[r]->gn_part[gs.slot][inst][me][threadIdx.x] = make_double2(a, b);
+                __threadfence_system();
+                __syncwarp();
+                if (static_cast<int>(threadIdx.x) < nr) {
+                    st_release_sys(&gs.peers.comm[threadIdx.x]->gn_flag[gs.slot][inst][me], e);
+                    spin_until_ge(&mine->gn_flag[gs.slot][inst][threadIdx.x], e);
+                }
+                __syncwarp();
+                a = 0.0;
+                b = 0.0;
+                for (int r = 0; r < nr; ++r) {
+                    const double2 v = __ldcv(&mine->gn_part[gs.slot][inst][r][threadIdx.x]);
+                    a += v.x;
+                    b += v.y;
+                }
+                n = static_cast<double>(gs.total_rows_per_inst) * cpg;
+            }
             const double mean = a / n;
             double var = b / n - mean * mean;
             if (var < 0.0) var = 0.0;
@@ -413,7 +439,7 @@ size_t gn_workspace_bytes(int rows_per_inst, int n_inst, int num_sms) {
 
 int groupnorm_silu(const __half* x, long long ldx, __half* y, long long ldy, long long rows, int C, int rows_per_inst,
                    const __half* gamma, const __half* beta, float eps, int silu, void* workspace, int num_sms,
-                   cudaStream_t stream, int phase) {
+                   cudaStream_t stream, int phase, const GnShard* shard) {
     if (C % 32 != 0 || C % 8 != 0 || C / 8 > kNormThreads || rows % rows_per_inst != 0 || (ldx & 7) != 0 || (ldy & 7) != 0) return -1;
     const int n_inst = static_cast<int>(rows / rows_per_inst);
     const int rpc = gn_rows_per_chunk(rows_per_inst, n_inst, num_sms);
@@ -423,9 +449,15 @@ int groupnorm_silu(const __half* x, long long ldx, __half* y, long long ldy, lon
     unsigned int* counters = reinterpret_cast<unsigned int*>(ws);
     float2* stats = reinterpret_cast<float2*>(ws + kCounterBytes);
     float2* partial = stats + static_cast<size_t>(n_inst) * kGroups;
+    GnShard gs;
+    memset(&gs, 0, sizeof(gs));
+    if (shard != nullptr && shard->peers.nranks > 1) {
+        if (n_inst > SHARD_MAX_INST || shard->slot < 0 || shard->slot >= SHARD_MAX_GN) return -4;
+        gs = *shard;
+    }
     if (phase != 2)
         launch_pdl(gn_stats_kernel, dim3(nchunks, n_inst), kNormThreads, stats_smem_bytes(C), stream, x, ldx, C, rows_per_inst,
-                   rpc, nchunks, eps, partial, counters, stats);
+                   rpc, nchunks, eps, partial, counters, stats, gs);
     if (phase == 1) return cudaGetLastError() == cudaSuccess ? 0 : -2;
     // rows per apply block: ~4 blocks per SM overall, at least 4 rows
     long long want_blocks = static_cast<long long>(num_sms) * 4;

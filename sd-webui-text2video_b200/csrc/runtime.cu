@@ -192,6 +192,11 @@ void Arena::free(char* p) {
     }
 }
 
+PlanShard::~PlanShard() {
+    for (int r = 0; r < SHARD_MAX_RANKS; ++r)
+        if (peer_slab[r] != nullptr && r != own_rank) cudaIpcCloseMemHandle(peer_slab[r]);
+}
+
 Plan::~Plan() {
     if (graph) cudaGraphExecDestroy(graph);
     if (slab) cudaFree(slab);
@@ -512,8 +517,18 @@ Tok linear(NetCtx& c, const Tok& x, const __half* w, int N, const __half* bias, 
     return y;
 }
 
-Tok group_norm(NetCtx& c, const Tok& x, const std::string& prefix, long long rows_per_inst, float eps, bool silu) {
+Tok group_norm(NetCtx& c, const Tok& x, const std::string& prefix, long long rows_per_inst, float eps, bool silu,
+               long long shard_total_rows) {
     Tok y = c.b->alloc(x.rows, x.C);
+    const ShardPeers* peers = shard_total_rows > 0 ? c.shard_peers : nullptr;
+    int slot = -1;
+    if (peers != nullptr && c.plan_shard != nullptr) {
+        slot = c.plan_shard->n_gn++;
+        if (slot >= SHARD_MAX_GN) {
+            set_error("frame-sharded plan: more than %d cross-rank GroupNorms", SHARD_MAX_GN);
+            c.b->error = -30;
+        }
+    }
     const __half* g = prm(c, prefix + ".weight");
     const __half* bt = prm(c, prefix + ".bias");
     void* ws = c.gn_ws;
@@ -522,8 +537,15 @@ Tok group_norm(NetCtx& c, const Tok& x, const std::string& prefix, long long row
     char lab[96];
     snprintf(lab, sizeof(lab), "gn_stats rows=%lld C=%d inst_rows=%lld", x.rows, x.C, rows_per_inst);
     c.b->step([=](cudaStream_t s) {
+        GnShard gs;
+        memset(&gs, 0, sizeof(gs));
+        if (peers != nullptr) {
+            gs.peers = *peers;          // read at launch: the peer table is filled by t2v_unet_shard_connect
+            gs.slot = slot;
+            gs.total_rows_per_inst = shard_total_rows;
+        }
         return groupnorm_silu(xx.p, xx.ld, y.p, y.ld, xx.rows, xx.C, static_cast<int>(rows_per_inst), g, bt, eps, silu ? 1 : 0,
-                              ws, sms, s, 1);
+                              ws, sms, s, 1, peers != nullptr ? &gs : nullptr);
     }, 1, STEP_NORM, 0.0, lab);
     snprintf(lab, sizeof(lab), "gn_apply rows=%lld C=%d inst_rows=%lld", x.rows, x.C, rows_per_inst);
     c.b->step([=](cudaStream_t s) {

@@ -5,12 +5,14 @@
 #include "common.cuh"
 #include "gemm_tc.cuh"
 #include "kernels.cuh"
+#include "shard.cuh"
 
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 #include <functional>
 #include <map>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -84,8 +86,23 @@ struct StepRec {
     std::string label;
 };
 
+// Frame-sharded plans (shard.cuh): host-side state the exchange steps read at LAUNCH time -- the peers' mapped slabs and
+// the byte offset of every exchange's destination buffer inside each peer's slab are only known after the ranks have
+// swapped their exports (t2v_unet_shard_connect), which happens after the plan is built and before its first replay.
+struct PlanShard {
+    int fb[SHARD_MAX_RANKS + 1] = {0};                 // frame partition of the clip
+    int n_xchg = 0, n_gn = 0;
+    long long dst_off[SHARD_MAX_XCHG] = {0};           // this rank's destination offsets (bytes into its slab)
+    long long peer_dst_off[SHARD_MAX_RANKS][SHARD_MAX_XCHG] = {{0}};
+    char* peer_slab[SHARD_MAX_RANKS] = {nullptr};      // peer_slab[rank] = own slab
+    bool connected = false;
+    int own_rank = 0;
+    ~PlanShard();
+};
+
 struct Plan {
     std::vector<StepRec> steps;
+    std::shared_ptr<PlanShard> shard;
     char* slab = nullptr;
     size_t slab_bytes = 0;
     double flops = 0.0;
@@ -125,6 +142,8 @@ struct NetCtx {
     Builder* b;
     cudaStream_t stream;      // weight-packing kernels are enqueued here while the plan is built
     void* gn_ws;              // zero-initialised groupnorm workspace (partials, stats, counters)
+    const ShardPeers* shard_peers = nullptr;   // frame-sharded clip: live peer table (filled by connect), else null
+    PlanShard* plan_shard = nullptr;
 };
 int round_up(int v, int m);
 // packed-weight accessors (created on first use, cached in the ParamStore until a parameter changes)
@@ -137,7 +156,9 @@ const __half* prm(NetCtx& c, const std::string& name);
 // recorded ops
 GemmProblem base_problem(const Tok& a, int K, const __half* w, int n_alloc, int N, const Tok& out);
 Tok linear(NetCtx& c, const Tok& x, const __half* w, int N, const __half* bias, const Tok* residual, int K = 0);
-Tok group_norm(NetCtx& c, const Tok& x, const std::string& prefix, long long rows_per_inst, float eps, bool silu);
+// shard_total_rows > 0: 5-D norm of a pixel-sharded clip -- the statistics span `shard_total_rows` rows per sample over all ranks
+Tok group_norm(NetCtx& c, const Tok& x, const std::string& prefix, long long rows_per_inst, float eps, bool silu,
+               long long shard_total_rows = 0);
 Tok layer_norm(NetCtx& c, const Tok& x, const std::string& prefix);
 // y = Linear(LayerNorm(x)) (+residual) with the normalisation folded into the GEMM: a row-statistics kernel (reads x once)
 // + one GEMM on the RAW rows whose epilogue applies rstd * (acc - mean * colsum) + bias'.  `w_src` [N, K] / `bias_src` are

@@ -1,0 +1,130 @@
+// FS <-> PS layout exchange over NVLink peer memory + epoch / barrier helpers (see shard.cuh).
+// Roofline: NVLink-bound.  Algorithmic bytes per launch and rank = rows * C * 2 * (P-1)/P sent and the same received
+// (e.g. 125 f x 32 x 32 x 320 ch, B = 2, 8 ranks: 17.9 MB each way per level-0 exchange).
+#include "shard.cuh"
+
+#include "common.cuh"
+
+namespace t2v {
+
+namespace {
+
+constexpr int kXThreads = 256;
+
+__global__ void __launch_bounds__(kXThreads) shard_exchange_kernel(const XchgParams p, int nblk) {
+    const int me = p.peers.rank, nr = p.peers.nranks;
+    ShardComm* mine = p.peers.comm[me];
+    const unsigned int e = *reinterpret_cast<volatile unsigned int*>(&mine->epoch);
+    const int k = p.slot;
+    if (blockIdx.x == 0) {
+        // ---- waiter block (scheduled first): announce that OUR destination buffer is dead (stream order: every kernel that used the memory it
+        // occupies has completed), then hold the kernel open until every peer's block has landed in it
+        if (threadIdx.x < nr && static_cast<int>(threadIdx.x) != me) st_release_sys(&p.peers.comm[threadIdx.x]->ready[k][me], e);
+        if (threadIdx.x < nr && static_cast<int>(threadIdx.x) != me) spin_until_ge(&mine->done[k][threadIdx.x], e);
+        return;
+    }
+    const int s = (blockIdx.x - 1) / nblk;           // destination rank of this block
+    const int j = (blockIdx.x - 1) - s * nblk;
+    const int C8 = p.C >> 3;
+    const int nf_me = p.fb[me + 1] - p.fb[me], np_me = p.pb[me + 1] - p.pb[me];
+    const int nf_s = p.fb[s + 1] - p.fb[s], np_s = p.pb[s + 1] - p.pb[s];
+    const int nf = p.to_ps ? nf_me : nf_s;           // frames in the (me -> s) block
+    const int np = p.to_ps ? np_s : np_me;           // pixels in it
+    const long long nvec = static_cast<long long>(p.B) * nf * np * C8;
+    if (s != me) {
+        if (threadIdx.x == 0) spin_until_ge(&mine->ready[k][s], e);      // s has released its destination buffer
+        __syncthreads();
+    }
+    const __half* src = p.src;
+    __half* dst = p.dst[s];
+    const long long stride = static_cast<long long>(nblk) * kXThreads;
+    constexpr int U = 4;
+    for (long long v0 = static_cast<long long>(j) * kXThreads + threadIdx.x; v0 < nvec; v0 += U * stride) {
+        uint4 val[U];
+        long long doff[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long long v = v0 + u * stride;
+            doff[u] = -1;
+            if (v < nvec) {
+                const long long row = v / C8;
+                const int vc = static_cast<int>(v - row * C8);
+                const long long bf = row / np;
+                const int pl = static_cast<int>(row - bf * np);
+                const int b = static_cast<int>(bf / nf);
+                const int fl = static_cast<int>(bf - static_cast<long long>(b) * nf);
+                long long srow, drow;
+                if (p.to_ps) {
+                    srow = (static_cast<long long>(b) * nf_me + fl) * p.P + p.pb[s] + pl;
+                    drow = (static_cast<long long>(b) * p.F + p.fb[me] + fl) * np_s + pl;
+                } else {
+                    srow = (static_cast<long long>(b) * p.F + p.fb[s] + fl) * np_me + pl;
+                    drow = (static_cast<long long>(b) * nf_s + fl) * p.P + p.pb[me] + pl;
+                }
+                val[u] = __ldg(reinterpret_cast<const uint4*>(src + srow * p.ld_src + vc * 8));
+                doff[u] = drow * p.ld_dst + vc * 8;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (doff[u] >= 0) *reinterpret_cast<uint4*>(dst + doff[u]) = val[u];
+    }
+    if (s != me) {
+        // publish: all of this block's stores, then count the block; the last block of destination s raises done[k][me] on s
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const unsigned int prev = atomicAdd(&mine->block_counter[k][s], 1u);
+            if (prev == static_cast<unsigned int>(nblk - 1)) {
+                mine->block_counter[k][s] = 0u;                              // self-cleaning for the next forward
+                __threadfence_system();
+                st_release_sys(&p.peers.comm[s]->done[k][me], e);
+            }
+        }
+    }
+}
+
+__global__ void shard_epoch_kernel(ShardComm* c) { c->epoch = c->epoch + 1u; }
+
+__global__ void shard_barrier_kernel(const ShardPeers peers, int slot) {
+    const int me = peers.rank;
+    const unsigned int e = *reinterpret_cast<volatile unsigned int*>(&peers.comm[me]->epoch);
+    const int t = threadIdx.x;
+    if (t < peers.nranks && t != me) {
+        st_release_sys(&peers.comm[t]->done[slot][me], e);
+        spin_until_ge(&peers.comm[me]->done[slot][t], e);
+    }
+}
+
+}  // namespace
+
+int shard_exchange(const XchgParams& p, int num_sms, cudaStream_t stream) {
+    if (p.peers.nranks < 2 || p.peers.nranks > SHARD_MAX_RANKS || p.slot < 0 || p.slot >= SHARD_MAX_XCHG || (p.C & 7) != 0 ||
+        (p.ld_src & 7) != 0 || (p.ld_dst & 7) != 0)
+        return -1;
+    const int nr = p.peers.nranks;
+    int max_nf = 0, max_np = 0;
+    for (int r = 0; r < nr; ++r) {
+        max_nf = max(max_nf, p.fb[r + 1] - p.fb[r]);
+        max_np = max(max_np, p.pb[r + 1] - p.pb[r]);
+    }
+    const long long vecs = static_cast<long long>(p.B) * max_nf * max_np * (p.C >> 3);
+    long long nblk = (vecs + 4 * kXThreads - 1) / (4 * kXThreads);
+    const long long cap = (2LL * num_sms + nr - 1) / nr;
+    if (nblk > cap) nblk = cap;
+    if (nblk < 1) nblk = 1;
+    shard_exchange_kernel<<<static_cast<unsigned>(nblk * nr + 1), kXThreads, 0, stream>>>(p, static_cast<int>(nblk));
+    return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
+int shard_bump_epoch(ShardComm* local, cudaStream_t stream) {
+    shard_epoch_kernel<<<1, 1, 0, stream>>>(local);
+    return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
+int shard_barrier(const ShardPeers& peers, int slot, cudaStream_t stream) {
+    shard_barrier_kernel<<<1, 32, 0, stream>>>(peers, slot);
+    return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
+}  // namespace t2v

@@ -41,11 +41,21 @@ struct t2v_unet {
     std::vector<std::string> plan_lru;                       // most recently used last; bounded (T2V_MAX_PLANS, default 4)
     bool taps_enabled = false;
     int last_launches = 0;
+    int last_exchanges = 0;
     // fixed staging for graph replay
     void* gn_ws = nullptr;
     size_t gn_ws_bytes = 0;
+    // frame-sharded clip (shard.cuh): one rank of `peers.nranks`, comm = this rank's IPC-shared flag / GroupNorm region
+    bool shard_on = false;
+    ShardPeers peers;
+    ShardComm* comm = nullptr;
+    t2v_unet() { memset(&peers, 0, sizeof(peers)); }
     ~t2v_unet() {
+        plans.clear();                      // closes the peers' slab mappings before the comm mappings go
         if (gn_ws) cudaFree(gn_ws);
+        for (int r = 0; r < SHARD_MAX_RANKS; ++r)
+            if (peers.comm[r] != nullptr && peers.comm[r] != comm) cudaIpcCloseMemHandle(peers.comm[r]);
+        if (comm) cudaFree(comm);
     }
 };
 
@@ -341,10 +351,60 @@ void expect_params_vc(t2v_unet* u) {
 struct Ctx : NetCtx {
     t2v_unet* u;
     int B, F, h, w, L;
+    int Fl;                   // frames held by this rank in the frame-sharded (FS) layout; = F when the clip is not sharded
+    int rank, nranks;         // (0, 1) when not sharded
+    char* slab;               // base of the plan's activation slab (exchange destinations are published as offsets into it)
     __half* emb;              // [B, E] time embedding (after time_embed MLP)
     __half* ctx;              // [B*L, ctx_dim] fixed staging of the text conditioning
     Plan* plan;
 };
+
+// pixels of a (hcur x wcur) level this rank owns in the pixel-sharded (PS) layout
+int own_pixels(const Ctx& c, int hcur, int wcur) {
+    if (c.nranks <= 1) return hcur * wcur;
+    int pb[SHARD_MAX_RANKS + 1];
+    shard_partition(hcur * wcur, c.nranks, pb);
+    return pb[c.rank + 1] - pb[c.rank];
+}
+
+// FS <-> PS transpose of a sharded clip's token matrix (shard.cu): every rank pushes its blocks into the peers' buffers
+Tok exchange(Ctx& c, const Tok& x, bool to_ps, int hcur, int wcur) {
+    const int P = hcur * wcur;
+    const int np = own_pixels(c, hcur, wcur);
+    const long long rows = to_ps ? static_cast<long long>(c.B) * c.F * np : static_cast<long long>(c.B) * c.Fl * P;
+    Tok y = c.b->alloc(rows, x.C);
+    PlanShard* ps = c.plan_shard;
+    const int k = ps->n_xchg++;
+    if (k >= SHARD_MAX_XCHG - 1) {          // the last slot is the barrier's
+        set_error("frame-sharded plan: more than %d layout exchanges", SHARD_MAX_XCHG - 1);
+        c.b->error = -31;
+        return y;
+    }
+    if (!c.b->dry()) ps->dst_off[k] = reinterpret_cast<char*>(y.p) - c.slab;
+    XchgParams xp;
+    memset(&xp, 0, sizeof(xp));
+    xp.slot = k;
+    xp.to_ps = to_ps ? 1 : 0;
+    xp.B = c.B; xp.F = c.F; xp.P = P; xp.C = x.C;
+    xp.ld_src = x.ld; xp.ld_dst = y.ld;
+    xp.src = x.p;
+    for (int r = 0; r <= c.nranks; ++r) xp.fb[r] = ps->fb[r];
+    shard_partition(P, c.nranks, xp.pb);
+    const ShardPeers* peers = c.shard_peers;
+    const int me = c.rank, nr = c.nranks, sms = c.b->sms();
+    __half* own = y.p;
+    char lab[96];
+    snprintf(lab, sizeof(lab), "exchange %s rows=%lld C=%d", to_ps ? "FS->PS" : "PS->FS", rows, x.C);
+    c.b->step([=](cudaStream_t s) {
+        if (!ps->connected) return -40;         // t2v_unet_shard_connect has not run for this plan
+        XchgParams q = xp;
+        q.peers = *peers;
+        for (int r = 0; r < nr; ++r)
+            q.dst[r] = r == me ? own : reinterpret_cast<__half*>(ps->peer_slab[r] + ps->peer_dst_off[r][k]);
+        return shard_exchange(q, sms, s);
+    }, 1, STEP_OTHER, 0.0, lab);
+    return y;
+}
 
 void tap(Ctx& c, const std::string& name, const Tok& t, int h, int w) {
     if (c.u->taps_enabled && !c.b->dry()) c.plan->taps[name] = {t, {h, w}};
@@ -353,9 +413,10 @@ void tap(Ctx& c, const std::string& name, const Tok& t, int h, int w) {
 // BasicTransformerBlock.forward (t2v_model.py:803-809): x += attn1(LN x); x += attn2(LN x, ctx); x += FF(LN x)
 // `temporal`: sequences run along frames for every pixel (both attentions are self-attention, :684-685);
 // otherwise sequences are the h*w tokens of a frame and attn2 attends to the prompt.
-Tok transformer_block(Ctx& c, Tok x, const std::string& p, int heads, int hcur, int wcur, bool temporal) {
+// P: rows between consecutive frames of a sample = pixels per frame (this rank's pixel range when the clip is sharded and
+// `temporal`: the matrix is then in the pixel-sharded layout)
+Tok transformer_block(Ctx& c, Tok x, const std::string& p, int heads, long long P, bool temporal) {
     const int C = x.C;
-    const long long P = static_cast<long long>(hcur) * wcur;
     const long long R = x.rows;
     const float scale = 0.125f;    // head_dim^-0.5, head_dim = 64 (t2v_model.py:530)
     for (int a = 0; a < 2; ++a) {
@@ -456,12 +517,15 @@ Tok transformer_block(Ctx& c, Tok x, const std::string& p, int heads, int hcur, 
 
 // SpatialTransformer.forward (:639-658, use_linear) / TemporalTransformer.forward (:716-767, Conv1d k=1 projections)
 Tok transformer(Ctx& c, const Tok& x, const Blk& blk, int hcur, int wcur, bool temporal) {
-    const long long P = static_cast<long long>(hcur) * wcur;
+    // temporal: rows (b, f, own pixels) -- all frames local; the 5-D GroupNorm's statistics span every rank's pixels
+    const long long Pfull = static_cast<long long>(hcur) * wcur;
+    const long long P = temporal ? own_pixels(c, hcur, wcur) : Pfull;
     const std::string& p = blk.prefix;
-    Tok n = group_norm(c, x, p + ".norm", temporal ? P * c.F : P, 1e-6f, false);
+    Tok n = group_norm(c, x, p + ".norm", temporal ? P * c.F : P, 1e-6f, false,
+                       (temporal && c.nranks > 1) ? Pfull * c.F : 0);
     Tok h0 = linear(c, n, prm(c, p + ".proj_in.weight"), blk.inner, prm(c, p + ".proj_in.bias"), nullptr);
     c.b->free(n);
-    Tok h3 = transformer_block(c, h0, p + ".transformer_blocks.0", blk.heads, hcur, wcur, temporal);
+    Tok h3 = transformer_block(c, h0, p + ".transformer_blocks.0", blk.heads, P, temporal);
     Tok y = linear(c, h3, prm(c, p + ".proj_out.weight"), blk.cin, prm(c, p + ".proj_out.bias"), &x);
     c.b->free(h3);
     return y;
@@ -485,7 +549,7 @@ Tok res_block(Ctx& c, const Tok& x, const Blk& blk, int hcur, int wcur) {
         c.b->step([=](cudaStream_t s) { return small_linear(emb, E, we, be, bc, bias1, Co, B, Co, E, 1, s); });
     }
     Tok a = group_norm(c, x, p + ".in_layers.0", P, 1e-5f, true);
-    Tok h = conv3x3(c, a, p + ".in_layers.2.weight", bias1, static_cast<int>(c.F * P), Co, Co, hcur, wcur, nullptr);
+    Tok h = conv3x3(c, a, p + ".in_layers.2.weight", bias1, static_cast<int>(c.Fl * P), Co, Co, hcur, wcur, nullptr);
     c.b->free(a);
     Tok bn_ = group_norm(c, h, p + ".out_layers.0", P, 1e-5f, true);
     c.b->free(h);
@@ -499,19 +563,28 @@ Tok res_block(Ctx& c, const Tok& x, const Blk& blk, int hcur, int wcur) {
     c.b->free(bn_);
     if (own_skip) c.b->free(skip);
     c.b->free_bytes(bias1);
-    // temporal conv block: 4 x [GN(5-D: statistics over all frames of a sample) -> SiLU -> Conv3d (3,1,1)] + identity
+    // temporal conv block: 4 x [GN(5-D: statistics over all frames of a sample) -> SiLU -> Conv3d (3,1,1)] + identity.
+    // Sharded clip: transpose to the pixel-sharded layout first -- all F frames of this rank's pixels are then local, the
+    // 3-tap conv and its zero padding at f = 0, F-1 need no halo; only the GroupNorm sums cross ranks.
+    const long long Pt = own_pixels(c, hcur, wcur);
+    if (c.nranks > 1) {
+        Tok hp = exchange(c, h2, true, hcur, wcur);
+        c.b->free(h2);
+        h2 = hp;
+    }
+    const long long Rt = h2.rows;
     const char* names[4] = {"conv1", "conv2", "conv3", "conv4"};
     const int idx[4] = {2, 3, 3, 3};
     Tok y = h2;
     for (int i = 0; i < 4; ++i) {
         const std::string tp = p + ".temopral_conv." + names[i];
-        Tok g = group_norm(c, y, tp + ".0", P * c.F, 1e-5f, true);
+        Tok g = group_norm(c, y, tp + ".0", Pt * c.F, 1e-5f, true, c.nranks > 1 ? P * c.F : 0);
         const std::string wn = tp + "." + std::to_string(idx[i]);
         const __half* w = w_conv(c, wn + ".weight", 3);
-        Tok y2 = c.b->alloc(R, Co);
+        Tok y2 = c.b->alloc(Rt, Co);
         GemmProblem pr = base_problem(g, Co, w, Co, Co, y2);
         pr.nd = 3;
-        pr.dim[0] = static_cast<int>(P);
+        pr.dim[0] = static_cast<int>(Pt);
         pr.dim[1] = c.F;
         pr.dim[2] = c.B;
         taps_temporal(pr);
@@ -714,9 +787,24 @@ int build(t2v_unet* u, Plan* plan, Arena* arena, bool dry, cudaStream_t stream, 
     c.u = u;
     c.B = B; c.F = F; c.h = h; c.w = w; c.L = L;
     c.emb = nullptr; c.ctx = nullptr; c.plan = plan;
+    c.Fl = F; c.rank = 0; c.nranks = 1; c.slab = plan->slab;
+    const bool sharded = u->shard_on && plan->shard != nullptr;
+    if (sharded) {                       // this rank's frames of the clip; temporal modules see all F of its pixel range
+        c.rank = u->peers.rank;
+        c.nranks = u->peers.nranks;
+        c.Fl = plan->shard->fb[c.rank + 1] - plan->shard->fb[c.rank];
+        c.shard_peers = &u->peers;
+        c.plan_shard = plan->shard.get();
+        plan->shard->n_xchg = 0;
+        plan->shard->n_gn = 0;
+        if (!dry) {
+            ShardComm* comm = u->comm;
+            bld.step([comm](cudaStream_t s) { return shard_bump_epoch(comm, s); }, 1, STEP_OTHER, 0.0, "epoch");
+        }
+    }
     const t2v_unet_config& cfg = u->cfg;
     const int E = cfg.dim * 4;
-    const long long R0 = static_cast<long long>(B) * F * h * w;
+    const long long R0 = static_cast<long long>(B) * c.Fl * h * w;
     const int cin_pad = round_up(cfg.in_dim, 8);
 
     // fixed I/O staging at the head of the slab (graph-replay friendly)
@@ -748,14 +836,34 @@ int build(t2v_unet* u, Plan* plan, Arena* arena, bool dry, cudaStream_t stream, 
     std::vector<std::pair<int, int>> xs_hw;
     Tok x = x0;
     bool x_is_io = true;
+    bool x_ps = false;                   // sharded clip: x is in the pixel-sharded layout (after a temporal module)
+    // x is released unless it is a pending skip connection or the I/O staging buffer
+    auto release = [&](const Tok& t) {
+        for (const Tok& s : xs)
+            if (s.p == t.p) return;
+        if (t.p == x0.p && x_is_io) return;
+        bld.free(t);
+    };
+    // sharded clip: bring x into the layout the next module works in (spatial modules: frame-sharded, temporal: pixel-sharded)
+    auto to_layout = [&](bool want_ps) {
+        if (!sharded || x_ps == want_ps) return;
+        Tok y = exchange(c, x, want_ps, hc, wc);
+        release(x);
+        x_is_io = false;
+        x = y;
+        x_ps = want_ps;
+    };
     auto run_block = [&](const std::vector<Blk>& blk) {
         for (const Blk& b : blk) {
             Tok y;
+            to_layout(b.kind == Blk::TT);
             switch (b.kind) {
                 case Blk::STEM:
                     y = conv3x3(c, x, b.prefix + ".weight", prm(c, b.prefix + ".bias"), 0, 0, b.cout, hc, wc, nullptr);
                     break;
-                case Blk::RES: y = cfg.arch == 1 ? res_block_vc(c, x, b, hc, wc) : res_block(c, x, b, hc, wc); break;
+                case Blk::RES:
+                    y = cfg.arch == 1 ? res_block_vc(c, x, b, hc, wc) : res_block(c, x, b, hc, wc);
+                    break;
                 case Blk::STT: y = stt_block(c, x, b, hc, wc); break;
                 case Blk::ST: y = transformer(c, x, b, hc, wc, false); break;
                 case Blk::TT: y = transformer(c, x, b, hc, wc, true); break;
@@ -770,23 +878,22 @@ int build(t2v_unet* u, Plan* plan, Arena* arena, bool dry, cudaStream_t stream, 
                     wc *= 2;
                     break;
             }
+            if (sharded && b.kind == Blk::RES) x_ps = true;     // res_block ends in the temporal conv block (pixel-sharded)
             tap(c, b.prefix, y, hc, wc);
-            // x is released unless it is a pending skip connection or the I/O staging buffer
-            bool is_skip = false;
-            for (const Tok& s : xs)
-                if (s.p == x.p) is_skip = true;
-            if (!is_skip && !x_is_io) bld.free(x);
+            release(x);
             x_is_io = false;
             x = y;
         }
     };
     for (auto& blk : u->ins) {
         run_block(blk);
+        to_layout(false);                // skip connections (and the next block's ResBlock) are frame-sharded
         xs.push_back(x);
         xs_hw.push_back({hc, wc});
     }
     run_block(u->mid);
     for (auto& blk : u->outs) {
+        to_layout(false);
         Tok skip = xs.back();
         xs.pop_back();
         xs_hw.pop_back();
@@ -806,6 +913,7 @@ int build(t2v_unet* u, Plan* plan, Arena* arena, bool dry, cudaStream_t stream, 
         x = cat;
         run_block(blk);
     }
+    to_layout(false);
     // head: GN -> SiLU -> Conv3x3 dim -> out_dim (t2v_model.py:321-323)
     Tok g = group_norm(c, x, "out.0", static_cast<long long>(hc) * wc * (cfg.arch == 1 ? F : 1), 1e-5f, true);
     bld.free(x);
@@ -820,7 +928,8 @@ std::map<Plan*, IO> g_io;
 
 Plan* get_plan(t2v_unet* u, int B, int F, int h, int w, int L, cudaStream_t stream) {
     char key[96];
-    snprintf(key, sizeof(key), "%d,%d,%d,%d,%d,%d", B, F, h, w, L, u->taps_enabled ? 1 : 0);
+    snprintf(key, sizeof(key), "%d,%d,%d,%d,%d,%d,%d/%d", B, F, h, w, L, u->taps_enabled ? 1 : 0, u->shard_on ? u->peers.rank : 0,
+             u->shard_on ? u->peers.nranks : 1);
     auto touch = [&](const std::string& k) {
         auto& l = u->plan_lru;
         l.erase(std::remove(l.begin(), l.end(), k), l.end());
@@ -884,8 +993,25 @@ Plan* get_plan(t2v_unet* u, int B, int F, int h, int w, int L, cudaStream_t stre
     std::unique_ptr<Plan> plan(new Plan());
     Arena arena;
     IO io;
+    if (u->shard_on) {
+        if (u->cfg.arch != 0 || u->taps_enabled) {
+            set_error("frame sharding is built for the ModelScope UNetSD (arch 0) without parity taps");
+            return nullptr;
+        }
+        int deepest = h * w;
+        for (int i = 1; i < u->cfg.n_mult; ++i) deepest = ((h + (1 << i) - 1) >> i) * ((w + (1 << i) - 1) >> i);
+        if (F < u->peers.nranks || deepest < u->peers.nranks || B > SHARD_MAX_INST) {
+            set_error("frame sharding over %d ranks needs >= %d frames, >= %d pixels at the deepest level (got %d) and B <= %d",
+                      u->peers.nranks, u->peers.nranks, u->peers.nranks, deepest, SHARD_MAX_INST);
+            return nullptr;
+        }
+        plan->shard.reset(new PlanShard());
+        plan->shard->own_rank = u->peers.rank;
+        shard_partition(F, u->peers.nranks, plan->shard->fb);
+    }
     {   // dry pass: peak activation bytes
         Plan scratch;
+        scratch.shard = plan->shard;
         arena.reset(nullptr, u->taps_enabled || getenv("T2V_ARENA_NO_REUSE") != nullptr);
         if (build(u, &scratch, &arena, true, stream, B, F, h, w, L, &io) != 0) return nullptr;
     }
@@ -990,6 +1116,15 @@ int t2v_unet_forward(t2v_unet* u, const void* x, int x_is_f32, const float* t, c
     const IO& io = g_io[plan];
     const t2v_unet_config& cfg = u->cfg;
     const int cin_pad = (cfg.in_dim + 7) / 8 * 8;
+    const int F_total = F;
+    if (u->shard_on) {                   // x / out hold this rank's frames only: [B, C, F_local, h, w]
+        if (!plan->shard->connected) {
+            set_error("frame-sharded forward before t2v_unet_shard_connect for this shape");
+            return -5;
+        }
+        F = plan->shard->fb[u->peers.rank + 1] - plan->shard->fb[u->peers.rank];
+    }
+    (void)F_total;
     int rc = ingest_latent(x, x_is_f32, io.x_tok, cin_pad, cin_pad, B, cfg.in_dim, F, h, w, 1.0f, stream);
     if (rc != 0) return rc;
     cudaMemcpyAsync(io.t, t, sizeof(float) * B, cudaMemcpyDeviceToDevice, stream);
@@ -1001,6 +1136,7 @@ int t2v_unet_forward(t2v_unet* u, const void* x, int x_is_f32, const float* t, c
         return rc;
     }
     u->last_launches = plan->launches + 2;
+    u->last_exchanges = plan->shard ? plan->shard->n_xchg : 0;
     const int out_ld = (cfg.out_dim % 8 == 0) ? cfg.out_dim : (cfg.out_dim + 7) / 8 * 8;
     return egress_latent(io.out_tok, out_ld, out, out_is_f32, B, cfg.out_dim, F, h, w, stream);
 }
@@ -1010,6 +1146,11 @@ double t2v_unet_flops(t2v_unet* u, int B, int F, int h, int w, int L) {
     Arena arena;
     arena.reset(nullptr, false);
     IO io;
+    if (u->shard_on) {                   // this rank's share of the clip's work
+        scratch.shard.reset(new PlanShard());
+        scratch.shard->own_rank = u->peers.rank;
+        shard_partition(F, u->peers.nranks, scratch.shard->fb);
+    }
     if (build(u, &scratch, &arena, true, nullptr, B, F, h, w, L, &io) != 0) return -1.0;
     return scratch.flops;
 }
@@ -1021,6 +1162,136 @@ int t2v_unet_profile(t2v_unet* u, int B, int F, int h, int w, int L, void* strea
     Plan* plan = get_plan(u, B, F, h, w, L, stream);
     if (!plan) return -1;
     return profile_plan(plan, stream, out13);
+}
+
+// ------------------------------------------------------------------------------------------ frame sharding (shard.cuh)
+int t2v_unet_shard_setup(t2v_unet* u, int rank, int nranks) {
+    if (nranks < 2 || nranks > SHARD_MAX_RANKS || rank < 0 || rank >= nranks) {
+        set_error("shard_setup: need 2 <= nranks <= %d and 0 <= rank < nranks (got %d / %d)", SHARD_MAX_RANKS, rank, nranks);
+        return -1;
+    }
+    if (u->cfg.arch != 0) {
+        set_error("frame sharding is built for the ModelScope UNetSD (arch 0)");
+        return -1;
+    }
+    if (u->comm == nullptr) {
+        if (cudaMalloc(&u->comm, sizeof(ShardComm)) != cudaSuccess || cudaMemset(u->comm, 0, sizeof(ShardComm)) != cudaSuccess) {
+            set_error("shard_setup: cudaMalloc of the communication region failed");
+            return -2;
+        }
+    }
+    for (auto& kv : u->plans) g_io.erase(kv.second.get());
+    u->plans.clear();
+    u->plan_lru.clear();
+    u->peers.rank = rank;
+    u->peers.nranks = nranks;
+    u->peers.comm[rank] = u->comm;
+    u->shard_on = true;
+    return 0;
+}
+
+int t2v_unet_shard_prepare(t2v_unet* u, int B, int F, int h, int w, int L, void* stream_, t2v_shard_export* out) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    if (!u->shard_on || out == nullptr) {
+        set_error("shard_prepare: call t2v_unet_shard_setup first");
+        return -1;
+    }
+    Plan* plan = get_plan(u, B, F, h, w, L, stream);
+    if (!plan) return -1;
+    memset(out, 0, sizeof(*out));
+    static_assert(sizeof(cudaIpcMemHandle_t) <= sizeof(out->comm_handle), "IPC handle size");
+    cudaIpcMemHandle_t hc, hs;
+    if (cudaIpcGetMemHandle(&hc, u->comm) != cudaSuccess || cudaIpcGetMemHandle(&hs, plan->slab) != cudaSuccess) {
+        set_error("shard_prepare: cudaIpcGetMemHandle failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return -2;
+    }
+    memcpy(out->comm_handle, &hc, sizeof(hc));
+    memcpy(out->slab_handle, &hs, sizeof(hs));
+    out->rank = u->peers.rank;
+    out->nranks = u->peers.nranks;
+    out->n_exchanges = plan->shard->n_xchg;
+    out->n_groupnorms = plan->shard->n_gn;
+    for (int k = 0; k < plan->shard->n_xchg; ++k) out->dst_offset[k] = plan->shard->dst_off[k];
+    return 0;
+}
+
+int t2v_unet_shard_connect(t2v_unet* u, int B, int F, int h, int w, int L, const t2v_shard_export* all, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    if (!u->shard_on || all == nullptr) {
+        set_error("shard_connect: call t2v_unet_shard_setup / t2v_unet_shard_prepare first");
+        return -1;
+    }
+    Plan* plan = get_plan(u, B, F, h, w, L, stream);
+    if (!plan) return -1;
+    PlanShard* ps = plan->shard.get();
+    const int me = u->peers.rank, nr = u->peers.nranks;
+    for (int r = 0; r < nr; ++r) {
+        const t2v_shard_export& e = all[r];
+        if (e.rank != r || e.nranks != nr || e.n_exchanges != ps->n_xchg || e.n_groupnorms != ps->n_gn) {
+            set_error("shard_connect: export of rank %d does not match this plan (rank %d/%d, %d exchanges, %d norms; here %d, %d)", r,
+                      e.rank, e.nranks, e.n_exchanges, e.n_groupnorms, ps->n_xchg, ps->n_gn);
+            return -2;
+        }
+        for (int k = 0; k < ps->n_xchg; ++k) ps->peer_dst_off[r][k] = e.dst_offset[k];
+        if (r == me) {
+            ps->peer_slab[r] = plan->slab;
+            continue;
+        }
+        if (u->peers.comm[r] == nullptr) {
+            cudaIpcMemHandle_t hc;
+            memcpy(&hc, e.comm_handle, sizeof(hc));
+            void* p = nullptr;
+            if (cudaIpcOpenMemHandle(&p, hc, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                set_error("shard_connect: cudaIpcOpenMemHandle(comm of rank %d) failed: %s", r, cudaGetErrorString(cudaGetLastError()));
+                return -3;
+            }
+            u->peers.comm[r] = reinterpret_cast<ShardComm*>(p);
+        }
+        if (ps->peer_slab[r] == nullptr) {
+            cudaIpcMemHandle_t hs;
+            memcpy(&hs, e.slab_handle, sizeof(hs));
+            void* p = nullptr;
+            if (cudaIpcOpenMemHandle(&p, hs, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                set_error("shard_connect: cudaIpcOpenMemHandle(slab of rank %d) failed: %s", r, cudaGetErrorString(cudaGetLastError()));
+                return -3;
+            }
+            ps->peer_slab[r] = reinterpret_cast<char*>(p);
+        }
+    }
+    ps->connected = true;
+    return 0;
+}
+
+int t2v_unet_shard_connected(t2v_unet* u, int B, int F, int h, int w, int L) {
+    if (!u->shard_on) return 0;
+    char key[96];
+    snprintf(key, sizeof(key), "%d,%d,%d,%d,%d,%d,%d/%d", B, F, h, w, L, 0, u->peers.rank, u->peers.nranks);
+    auto it = u->plans.find(key);
+    return (it != u->plans.end() && it->second->weights_version == u->params.version() && it->second->shard &&
+            it->second->shard->connected) ? 1 : 0;
+}
+
+int t2v_unet_shard_barrier(t2v_unet* u, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    if (!u->shard_on) return -1;
+    for (int r = 0; r < u->peers.nranks; ++r)
+        if (u->peers.comm[r] == nullptr) {
+            set_error("shard_barrier: rank %d is not connected", r);
+            return -2;
+        }
+    int rc = shard_bump_epoch(u->comm, stream);
+    if (rc != 0) return rc;
+    return shard_barrier(u->peers, SHARD_MAX_XCHG - 1, stream);
+}
+
+int t2v_unet_shard_info(t2v_unet* u, int F, int* frame_begin, int* frame_end, int* n_exchanges) {
+    if (!u->shard_on) return -1;
+    int fb[SHARD_MAX_RANKS + 1];
+    shard_partition(F, u->peers.nranks, fb);
+    if (frame_begin) *frame_begin = fb[u->peers.rank];
+    if (frame_end) *frame_end = fb[u->peers.rank + 1];
+    if (n_exchanges) *n_exchanges = u->last_exchanges;
+    return 0;
 }
 
 int t2v_unet_enable_taps(t2v_unet* u, int on) {

@@ -29,6 +29,12 @@ SIGNATURES = {
     't2v_unet_profile': (c_int, [P, c_int, c_int, c_int, c_int, c_int, P, C.POINTER(c_double)]),
     't2v_unet_read_tap': (c_ll, [P, c_char_p, P, c_ll, P]),
     't2v_unet_enable_taps': (c_int, [P, c_int]),
+    't2v_unet_shard_setup': (c_int, [P, c_int, c_int]),
+    't2v_unet_shard_prepare': (c_int, [P, c_int, c_int, c_int, c_int, c_int, P, P]),
+    't2v_unet_shard_connect': (c_int, [P, c_int, c_int, c_int, c_int, c_int, P, P]),
+    't2v_unet_shard_connected': (c_int, [P, c_int, c_int, c_int, c_int, c_int]),
+    't2v_unet_shard_barrier': (c_int, [P, P]),
+    't2v_unet_shard_info': (c_int, [P, c_int, C.POINTER(c_int), C.POINTER(c_int), C.POINTER(c_int)]),
     't2v_vae_create': (c_int, [P, C.POINTER(P)]),
     't2v_vae_destroy': (None, [P]),
     't2v_vae_set_param': (c_int, [P, c_char_p, P, c_int, c_int, C.POINTER(C.c_int64), P]),
@@ -65,6 +71,12 @@ class UNetConfigC(C.Structure):
                 ('dim_mult', c_int * 8), ('n_mult', c_int), ('num_heads', c_int), ('head_dim', c_int),
                 ('num_res_blocks', c_int), ('attn_scales', c_float * 8), ('n_attn_scales', c_int), ('arch', c_int),
                 ('temporal_length', c_int)]
+
+
+class ShardExportC(C.Structure):
+    """t2v_shard_export (include/t2v_b200.h): what the ranks of a frame-sharded clip swap once per shape."""
+    _fields_ = [('comm_handle', C.c_ubyte * 64), ('slab_handle', C.c_ubyte * 64), ('rank', c_int), ('nranks', c_int),
+                ('n_exchanges', c_int), ('n_groupnorms', c_int), ('dst_offset', c_ll * 192)]
 
 
 class VAEConfigC(C.Structure):

@@ -7,7 +7,13 @@ Opt-in second mode (T2V_CFG_SPLIT=1, even world size): the classifier-free-guida
 forwards, gaussian_sampler.py:161-162 / ddim/sampler.py:176-179 / ddim.py:216-217 -- is split over a PAIR of GPUs (even
 rank = conditional, odd rank = unconditional) with one all-gather of the two eps tensors per step (196 KB at 24f x 256^2)
 inside the pair; both ranks then apply the identical fused update, so the latent stays replicated.  This halves the
-latency of ONE clip (B = 1 forward per GPU instead of B = 2) at the cost of half the clips in flight; SURVEY.md 8e."""
+latency of ONE clip (B = 1 forward per GPU instead of B = 2) at the cost of half the clips in flight; SURVEY.md 8e.
+
+Third mode, frame sharding (BASELINE config 4: ONE 125-frame clip over 8 GPUs, `FrameShardedClip` below): every rank keeps
+only its frames of the latent through the whole sampling loop -- the scheduler updates are element-wise -- and the UNet
+exchanges activations between the ranks inside its own kernels over NVLink peer memory (csrc/shard.cu; no NCCL call per
+step).  NCCL is used for exactly what the north-star names: ONE all-gather of the final latent before the VAE decode (each
+rank then decodes its own frames) and one all-gather of the decoded frames."""
 import os
 
 import torch
@@ -101,3 +107,76 @@ def pair_callback(callback, *args):
     if int(flag.item()) != 0:
         from .samplers import InterruptedException
         raise InterruptedException()
+
+
+# ------------------------------------------------------------------------------------------------ frame-sharded clip
+_frame_shard = None          # the active FrameShardedClip while its sampling loop runs (samplers draw noise through it)
+
+
+def frame_bounds(F, world_size):
+    """Balanced contiguous frame ranges, larger ones first -- the same partition csrc/shard.cuh::shard_partition computes."""
+    out, off = [], 0
+    for r in range(world_size):
+        out.append(off)
+        off += F // world_size + (1 if r < F % world_size else 0)
+    return out + [off]
+
+
+def step_noise(like):
+    """Per-step sampler noise (eta > 0).  Frame-sharded: every rank draws the FULL clip's noise from its (identically seeded)
+    CUDA generator and keeps its frames, so the result does not depend on the number of ranks."""
+    fs = _frame_shard
+    if fs is None:
+        return pair_shared(torch.randn_like(like))
+    full = torch.randn((like.shape[0], like.shape[1], fs.F) + tuple(like.shape[3:]), device=like.device, dtype=like.dtype)
+    return full[:, :, fs.f0:fs.f1].contiguous()
+
+
+class FrameShardedClip(object):
+    """Drives ONE clip over the ranks of `group`: slices x_T, runs the unchanged scheduler classes on this rank's frames
+    (the UNet mirror is in shard mode), gathers the final latent once, decodes this rank's frames, gathers the frames."""
+
+    def __init__(self, sd_model, autoencoder, group=None):
+        self.sd_model, self.autoencoder, self.group = sd_model, autoencoder, group
+        self.rank, self.ws = dist.get_rank(group), dist.get_world_size(group)
+        if getattr(sd_model, '_shard', None) is None:
+            sd_model.shard_setup(group)
+        self.F = self.f0 = self.f1 = None
+
+    def begin(self, F, seed=None):
+        global _frame_shard
+        self.F = int(F)
+        b = frame_bounds(self.F, self.ws)
+        self.f0, self.f1 = b[self.rank], b[self.rank + 1]
+        self.sd_model.set_clip_frames(self.F)
+        if seed is not None:
+            torch.cuda.manual_seed(int(seed))          # identical per-step noise streams on every rank (eta > 0)
+        _frame_shard = self
+
+    def end(self):
+        global _frame_shard
+        _frame_shard = None
+
+    def local(self, x_full):
+        return x_full[:, :, self.f0:self.f1].contiguous()
+
+    def _gather_frames(self, t, dim):
+        """all-gather of per-rank frame slices with ragged counts (padded to the largest slice)."""
+        b = frame_bounds(self.F, self.ws)
+        nmax = max(b[r + 1] - b[r] for r in range(self.ws))
+        pad_shape = list(t.shape)
+        pad_shape[dim] = nmax
+        buf = torch.zeros(pad_shape, dtype=t.dtype, device=t.device)
+        buf.narrow(dim, 0, t.shape[dim]).copy_(t)
+        out = [torch.empty_like(buf) for _ in range(self.ws)]
+        dist.all_gather(out, buf, group=self.group)
+        return torch.cat([out[r].narrow(dim, 0, b[r + 1] - b[r]) for r in range(self.ws)], dim=dim)
+
+    def gather_latent(self, x_local):
+        """THE all-gather before the VAE: [1, 4, F_local, h, w] -> [1, 4, F, h, w] on every rank."""
+        return self._gather_frames(x_local.contiguous(), 2)
+
+    def decode(self, x0_full, z_scale):
+        """Frame-sharded VAE: this rank decodes its own frames (the decoder is per-frame), then one all-gather of uint8 frames."""
+        mine = self.autoencoder.decode_video(self.local(x0_full), z_scale, as_uint8=True)      # [F_local, H, W, 3]
+        return self._gather_frames(mine, 0)

@@ -210,14 +210,70 @@ class UNetSD(_NativeModule):
             else:
                 self.register_buffer(name, f32(val))
 
+    # -- frame-sharded clip (include/t2v_b200.h "frame-sharded clip"; t2v_b200/distributed.py drives it)
+    def shard_setup(self, group=None):
+        """Makes this module one rank of a frame-sharded denoiser: ONE clip split over the ranks of `group` (default: the
+        world), each holding `frame_range(F)` of the latent.  forward() then takes / returns this rank's frames only."""
+        import torch.distributed as dist
+        rank, ws = dist.get_rank(group), dist.get_world_size(group)
+        _lib.check(_lib.lib().t2v_unet_shard_setup(self._handle, rank, ws), 'unet_shard_setup')
+        self._shard = (group, rank, ws)
+        self._shard_frames = None
+
+    def set_clip_frames(self, F_total):
+        """Frames of the WHOLE clip the following forwards belong to (the samplers only ever see this rank's slice)."""
+        self._shard_frames = int(F_total)
+
+    def frame_range(self, F):
+        b, e = C.c_int(0), C.c_int(0)
+        _lib.check(_lib.lib().t2v_unet_shard_info(self._handle, int(F), C.byref(b), C.byref(e), None), 'unet_shard_info')
+        return b.value, e.value
+
+    def num_exchanges(self, F):
+        n = C.c_int(0)
+        _lib.check(_lib.lib().t2v_unet_shard_info(self._handle, int(F), None, None, C.byref(n)), 'unet_shard_info')
+        return n.value
+
+    def _shard_connect(self, B, F, h, w, L):
+        """Builds this rank's plan for the shape and swaps the exports (IPC handles of the activation slab + destination
+        offsets) with the other ranks: ONE byte all-gather per shape, never per forward."""
+        import torch.distributed as dist
+        l = _lib.lib()
+        group, rank, ws = self._shard
+        if l.t2v_unet_shard_connected(self._handle, B, F, h, w, L):
+            return
+        mine = _lib.ShardExportC()
+        _lib.check(l.t2v_unet_shard_prepare(self._handle, B, F, h, w, L, _lib.stream_ptr(), C.byref(mine)), 'unet_shard_prepare')
+        n = C.sizeof(_lib.ShardExportC)
+        buf = torch.frombuffer(bytearray(bytes(mine)), dtype=torch.uint8).clone()
+        backend = dist.get_backend(group)
+        if backend == 'nccl':
+            buf = buf.cuda()
+        out = [torch.empty_like(buf) for _ in range(ws)]
+        dist.all_gather(out, buf, group=group)
+        arr = (_lib.ShardExportC * ws)()
+        for r in range(ws):
+            C.memmove(C.byref(arr, r * n), bytes(out[r].cpu().numpy().tobytes()), n)
+        _lib.check(l.t2v_unet_shard_connect(self._handle, B, F, h, w, L, arr, _lib.stream_ptr()), 'unet_shard_connect')
+        torch.cuda.current_stream().synchronize()
+        dist.barrier(group=group)               # every rank has mapped every slab before anyone starts pushing into them
+
     @torch.no_grad()
-    def forward(self, x, t, y, **ignored):
-        """eps = UNetSD(x, t, y).  Returns fp16 [B, out_dim, F, h, w] (what the reference returns under autocast)."""
+    def forward(self, x, t, y, F_total=None, **ignored):
+        """eps = UNetSD(x, t, y).  Returns fp16 [B, out_dim, F, h, w] (what the reference returns under autocast).
+        Frame-sharded (after shard_setup): x holds this rank's frames of an `F_total`-frame clip, so does the result."""
         if x.dim() != 5:
             raise ValueError('x must be [B, C, F, h, w]')
         self.sync_weights()
         l = _lib.lib()
         B, Cc, F, h, w = x.shape
+        if getattr(self, '_shard', None) is not None:
+            F_total = F_total if F_total is not None else self._shard_frames
+            if F_total is None:
+                raise ValueError('frame-sharded UNetSD: call set_clip_frames(F) or pass F_total (frames of the whole clip)')
+            b0, b1 = self.frame_range(F_total)
+            if F != b1 - b0:
+                raise ValueError(f'this rank holds frames [{b0}, {b1}) of {F_total}; got {F} frames')
         if Cc != self.in_dim:
             raise ValueError(f'expected {self.in_dim} latent channels, got {Cc}')
         if x.dtype not in (torch.float32, torch.float16):
@@ -234,6 +290,9 @@ class UNetSD(_NativeModule):
         if y.shape[2] != self.context_dim:
             raise ValueError(f'context dim {y.shape[2]} != {self.context_dim}')
         out = torch.empty((B, self.out_dim, F, h, w), device=x.device, dtype=torch.float16)
+        if getattr(self, '_shard', None) is not None:
+            self._shard_connect(B, F_total, h, w, y.shape[1])
+            F = F_total
         rc = l.t2v_unet_forward(self._handle, _lib.ptr(x), int(x.dtype == torch.float32), _lib.ptr(t), _lib.ptr(y),
                                 _lib.ptr(out), 0, B, F, h, w, y.shape[1], _lib.stream_ptr())
         _lib.check(rc, 'unet_forward')

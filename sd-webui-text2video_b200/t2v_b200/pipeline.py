@@ -85,6 +85,14 @@ class TextToVideoSynthesis(object):
         self.clip_encoder = clip_encoder
         self.noise_gen = torch.Generator(device='cpu')
         self.last_tensor = None
+        self.frame_shard = None
+
+    def enable_frame_shard(self, group=None):
+        """ONE clip over the ranks of `group` (BASELINE config 4): every rank calls infer() with the same arguments and gets
+        the same finished clip; the denoiser exchanges activations over NVLink inside its kernels (distributed.py)."""
+        from .distributed import FrameShardedClip
+        self.frame_shard = FrameShardedClip(self.sd_model, self.autoencoder, group)
+        return self.frame_shard
 
     # ------------------------------------------------------------------------------------------ conditioning
     def preprocess(self, prompt, n_prompt, steps=None):
@@ -116,12 +124,28 @@ class TextToVideoSynthesis(object):
                 latents = latents.half()            # also rounds the scheduler's entry latent (`.to(dtype=latent.dtype)`)
         latents, noise, shape = self.diffusion.get_noise(1, 4, frames, height, width, seed=seed, latents=latents)
         self.diffusion.get_sampler(sampler, return_sampler=False)
-        x0 = self.diffusion.sample_loop(steps=steps, strength=strength, eta=eta, conditioning=c,
-                                        unconditional_conditioning=uc, batch_size=1, guidance_scale=scale,
-                                        latents=latents, shape=shape, noise=noise, is_vid2vid=is_vid2vid,
-                                        sampler_name=sampler, mask=mask)
-        self.last_tensor = x0
-        frames_u8 = self.autoencoder.decode_video(x0, 1.0 / SCALE_FACTOR, as_uint8=True)     # [F, H, W, 3] RGB, device
+        fs = self.frame_shard
+        if fs is not None:
+            # frame-sharded clip: the (identical, CPU-seeded) x_T is cut to this rank's frames; the scheduler never sees more
+            fs.begin(shape[2], seed)
+            noise = fs.local(noise)
+            latents = fs.local(latents) if latents is not None else None
+            shape = tuple(noise.shape)
+        try:
+            x0 = self.diffusion.sample_loop(steps=steps, strength=strength, eta=eta, conditioning=c,
+                                            unconditional_conditioning=uc, batch_size=1, guidance_scale=scale,
+                                            latents=latents, shape=shape, noise=noise, is_vid2vid=is_vid2vid,
+                                            sampler_name=sampler, mask=mask)
+        finally:
+            if fs is not None:
+                fs.end()
+        if fs is not None:
+            x0 = fs.gather_latent(x0)               # the single NCCL all-gather before the VAE
+            self.last_tensor = x0
+            frames_u8 = fs.decode(x0, 1.0 / SCALE_FACTOR)
+        else:
+            self.last_tensor = x0
+            frames_u8 = self.autoencoder.decode_video(x0, 1.0 / SCALE_FACTOR, as_uint8=True)     # [F, H, W, 3] RGB, device
         host = torch.empty(frames_u8.shape, dtype=torch.uint8, pin_memory=True)
         host.copy_(frames_u8, non_blocking=True)                                              # the one D2H of the clip
         torch.cuda.current_stream().synchronize()

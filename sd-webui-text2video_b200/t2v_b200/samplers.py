@@ -164,14 +164,18 @@ class GaussianDiffusion(object):
             sig = eta * torch.sqrt(((1 - alp) / (1 - al)) * (1 - al / alp))
             direction = torch.sqrt(1 - alp - sig ** 2)
             nz_mask = 1.0 if tv != 0 else 0.0
-            noise = _dist.pair_shared(torch.randn_like(xt))   # drawn every step, as the reference does (:279)
+            noise = _dist.step_noise(xt)                      # drawn every step, as the reference does (:279)
             xt = _step_kernel(xt, e_c, e_u, 1.0 if unguided else g, self.guided_channels(xt.shape[1]), 0,
                               (sr, srm1, torch.sqrt(alp), direction, nz_mask * sig), noise,
                               cfg_fp16=(e_c.dtype == torch.float16))
             if hasattr(self, 'inpaint_masking'):
                 # the reference overwrites `mask` with t.ne(0)... (:281), so its inpaint hook runs -- and draws one more
                 # randn_like -- on EVERY step whenever the hook is attached, whether or not the caller passed a mask (:285-291)
-                torch.randn_like(xt)
+                # (frame-sharded clips draw the full clip's shape so that every rank's generator advances identically)
+                if _dist._frame_shard is not None:
+                    _dist.step_noise(xt)
+                else:
+                    torch.randn_like(xt)
             if callback is not None:
                 _dist.pair_callback(callback, step)
         return xt
@@ -244,7 +248,7 @@ class DDIMSampler(object):
                 e_c, e_u = _eval_pair(self.model, img, ts, c, uc)
             a_t, a_prev = _f32(self.ddim_alphas[index]), _f32(self.ddim_alphas_prev[index])
             sigma, s1m = _f32(self.ddim_sigmas[index]), _f32(self.ddim_sqrt_one_minus_alphas[index])
-            noise = _dist.pair_shared(torch.randn(img.shape, device=img.device))
+            noise = _dist.step_noise(img)
             img = _step_kernel(img, e_c, e_u, 1.0 if unguided else g, img.shape[1], 1,
                                (s1m, a_t.sqrt(), a_prev.sqrt(), (1.0 - a_prev - sigma ** 2).sqrt(), sigma * temperature),
                                noise, cfg_fp16=(e_c.dtype == torch.float16))

@@ -87,3 +87,59 @@ def test_cfg_pair_split_world2():
     assert res[0][1] == (0, 1) and res[1][1] == (0, 1)              # one clip-rendering unit (the pair)
     assert res[0][2] == [0.25] and res[1][2] == [-0.5]              # even rank: conditional, odd rank: unconditional
     assert all(r[3] == 0.0 and r[4] == 0.0 for r in res)
+
+
+def _frame_shard_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from t2v_b200 import distributed as D
+
+    class FakeVAE:
+        def decode_video(self, z, z_scale, as_uint8=True):            # [1, 4, n, h, w] -> [n, 2, 2, 3] "frames" tagged by content
+            n = z.shape[2]
+            return (z[0, 0, :, 0, 0].view(n, 1, 1, 1).expand(n, 2, 2, 3) * z_scale).to(torch.uint8)
+
+    class FakeUNet:
+        _shard = ('g', rank, world)
+
+        def set_clip_frames(self, F):
+            self.F = F
+    fs = D.FrameShardedClip(FakeUNet(), FakeVAE())
+    F = 7
+    full = torch.arange(F, dtype=torch.float32).view(1, 1, F, 1, 1).expand(1, 4, F, 3, 2).contiguous()
+    fs.begin(F, seed=None)
+    try:
+        mine = fs.local(full)
+        assert mine.shape[2] == D.frame_bounds(F, world)[rank + 1] - D.frame_bounds(F, world)[rank]
+        torch.manual_seed(5)
+        n1 = D.step_noise(mine)
+        torch.manual_seed(5)
+        ref = torch.randn(full.shape)
+        assert torch.equal(n1, ref[:, :, fs.f0:fs.f1])                # every rank draws the full clip's noise, keeps its frames
+        back = fs.gather_latent(mine)
+        frames = fs.decode(back, 2.0)
+    finally:
+        fs.end()
+    q.put((rank, torch.equal(back, full), frames[:, 0, 0, 0].tolist()))
+    dist.destroy_process_group()
+
+
+def test_frame_shard_host_logic_world3():
+    """Ragged frame ranges (7 frames over 3 ranks), the latent all-gather before the VAE and the frame-sharded decode +
+    frame gather, on gloo."""
+    import torch.multiprocessing as mp
+    from t2v_b200 import distributed as D
+    assert D.frame_bounds(125, 8) == [0, 16, 32, 48, 64, 80, 95, 110, 125]
+    assert D.frame_bounds(7, 3) == [0, 3, 5, 7]
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_frame_shard_worker, args=(r, 3, port, q)) for r in range(3)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=30)
+    for rank, ok, frames in res:
+        assert ok and frames == [0, 2, 4, 6, 8, 10, 12], (rank, ok, frames)

@@ -20,7 +20,7 @@ from parity_util import report  # noqa: E402
 
 pytestmark = pytest.mark.gpu
 
-RMS_GATE, MAX_GATE = 4e-3, 1.6e-2
+RMS_GATE, MAX_GATE = 4e-3, 6e-3      # measured <= 2.9e-3 / 3.5e-3 over every model-level case (profiles/r02_parity_report.jsonl)
 
 
 def errs(a, b):
@@ -121,7 +121,7 @@ def test_vae_decode_vs_reference_fixture(gold_dir):
     out = vae.decode(z.cuda())
     e = errs(out, g['out'])
     report('vae_decode', max=e[0], rms=e[1])
-    assert e[1] < 5e-3 and e[0] < 2e-2, e
+    assert e[1] < 2.1e-3 and e[0] < 2.4e-3, e          # measured 1.38e-3 / 1.57e-3
     # batched video path + fused uint8 conversion == tensor2vid on the float output
     z5 = (z * 0.18215).view(1, 2, 4, 8, 16).permute(0, 2, 1, 3, 4).contiguous()
     u8 = vae.decode_video(z5.cuda(), 1.0 / 0.18215, as_uint8=True).cpu()

@@ -58,7 +58,7 @@ def test_short_trajectory_and_decode_vs_oracle(pipe):
                                   c.float(), uc.float(), 5.0)
     err = (latent.cpu() - ref).abs().max() / ref.abs().max()
     report('pipeline:ddim_gaussian_4steps_tiny', max=float(err))
-    assert err < 3e-2, err                      # 4 steps x 2 fp16 forwards each, vs fp32 oracle
+    assert err < 6e-3, err                      # 4 steps x 2 fp16 forwards each, vs fp32 oracle (measured 3.8e-3)
     dec = VO.vae_decode({k: v.half().float() for k, v in Wv.items()}, VO.VAEConfig(),
                         (ref[0].permute(1, 0, 2, 3) / 0.18215))
     ref_u8 = VO.tensor2vid_u8(dec.permute(1, 0, 2, 3).unsqueeze(0))          # [F, H, W, 3] RGB

@@ -53,7 +53,7 @@ def test_ddim_trajectory_vs_oracle(ldm, S, scale, eta):
                             eta=eta, noise_gen=torch.Generator('cpu').manual_seed(11))
     err = (out.cpu() - ref).abs().max() / ref.abs().max()
     report(f'vc_ddim_tiny:S{S}_g{scale}_eta{eta}', max=float(err))
-    assert err < 3e-2, err
+    assert err < 5e-3, err                      # measured <= 3.2e-3
     assert 'x_inter' in inter
 
 
