@@ -57,21 +57,33 @@ __device__ __forceinline__ float gelu_erf(float x) {
     return x * (x < 0.f ? q : 1.0f - q);
 }
 
-template <int BN, bool GEGLU, int CG>
+// BS = "B-stationary": the CTA keeps the WHOLE weight slice of its N-tile (all taps x K chunks) resident in shared memory and
+// walks M-tiles of that N-tile only, so per tile just the A box moves through the ring.  Chosen by gemm_plan for the K = 320
+// layers (level 0: 30 % of the forward's GEMM time at 15-37 % tensor pipe): those are bound by the aggregate L2 -> SM operand
+// stream (~12 TB/s, profiles/r01_gemm_isolation.txt), and with BN = 160 the B box (100 KB) outweighs the A box (80 KB) --
+// re-fetching it for every tile was more than half of the traffic.
+template <int BN, bool GEGLU, int CG, bool BS = false>
 __global__ void __launch_bounds__(n_threads(GEGLU), 1) gemm_tc_kernel(const __grid_constant__ GemmDesc g) {
     constexpr int EW = epi_warps(GEGLU);
     using C = Cfg<BN, CG>;
+    static_assert(!BS || CG == 1, "B-stationary tiles are single-CTA");
+    constexpr int kBarStages = BS ? 8 : C::kStages;                 // barrier slots (BS: ring depth is a run-time value <= 8)
     const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;      // position in the CTA pair
     const bool leader = rank == 0;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);      // SWIZZLE_128B atoms need 1024 B alignment
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (BS ? kSmemBudget : C::kStages * C::kStageBytes));
     uint64_t* full = bars;                       // [kStages] TMA -> MMA
-    uint64_t* empty = bars + C::kStages;         // [kStages] MMA -> TMA
-    uint64_t* tfull = bars + 2 * C::kStages;     // [2] MMA -> epilogue
+    uint64_t* empty = bars + kBarStages;         // [kStages] MMA -> TMA
+    uint64_t* tfull = bars + 2 * kBarStages;     // [2] MMA -> epilogue
     uint64_t* tempty = tfull + 2;                // [2] epilogue -> MMA
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    uint64_t* bfull = tempty + 4;                // BS: the resident weight slice has landed (<= 8 * 20 + 8 = 168 B < 256)
+    // BS smem map: [resident B: k_total chunks of BN x 64][A ring: bs_stages x 16 KB] ... barriers at the fixed ring budget
+    const int nst = BS ? g.bs_stages : C::kStages;
+    uint8_t* const sB_res = smem;
+    uint8_t* const sA_ring = smem + (BS ? g.ntaps * g.k_chunks * C::kBBytes : 0);
     float* bias_s = reinterpret_cast<float*>(bars) + 64;         // [2 accumulator stages][256] fp32 bias tile (256 B after the barriers)
     float* csum_s = bias_s + 512;                                // [2][256] column sums of the gamma-scaled weights (GEMM_LN)
     uint8_t* stage_s = reinterpret_cast<uint8_t*>(bars) + 4608;  // [8 warps][32 rows][64 B], 512 B aligned (SWIZZLE_64B atoms)
@@ -82,10 +94,11 @@ __global__ void __launch_bounds__(n_threads(GEGLU), 1) gemm_tc_kernel(const __gr
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&g.map_a);
         tma_prefetch_desc(&g.map_b);
-        for (int i = 0; i < C::kStages; ++i) {
+        for (int i = 0; i < kBarStages; ++i) {
             mbar_init(&full[i], 1);
             mbar_init(&empty[i], 1);
         }
+        if constexpr (BS) mbar_init(bfull, 1);
         mbar_init(&tfull[0], 1);
         mbar_init(&tfull[1], 1);
         mbar_init(&tempty[0], EW * CG);           // the leader's barrier also collects the peer's epilogue warps
@@ -107,22 +120,35 @@ __global__ void __launch_bounds__(n_threads(GEGLU), 1) gemm_tc_kernel(const __gr
     const int pairs_m = (g.tiles_m + CG - 1) / CG;
     const int nsplit = g.splits > 1 ? g.splits : 1;
     const int total_pairs = pairs_m * g.tiles_n * nsplit;      // work items: (pair of M-tiles, N-tile, K split)
-    const int first_pair = blockIdx.x / CG;
-    const int pair_stride = gridDim.x / CG;
     const int k_total = g.ntaps * g.k_chunks;
     const int k_per = g.splits > 1 ? g.k_per_split : k_total;
+    // BS: this CTA owns N-tile bs_tn and walks the M-tiles first_pair, first_pair + pair_stride, ... (work item = M-tile)
+    const int bs_tn = BS ? static_cast<int>(blockIdx.x) % g.tiles_n : 0;
+    const int first_pair = BS ? static_cast<int>(blockIdx.x) / g.tiles_n : static_cast<int>(blockIdx.x) / CG;
+    const int pair_stride = BS ? (static_cast<int>(gridDim.x) - bs_tn + g.tiles_n - 1) / g.tiles_n : static_cast<int>(gridDim.x) / CG;
+    const int total_items = BS ? g.tiles_m : total_pairs;
 
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int wi = first_pair; wi < total_pairs; wi += pair_stride) {
-                const int sp = wi % nsplit;
+            if constexpr (BS) {
+                if (first_pair < total_items) {        // the resident weight slice: every (tap, K chunk) box of N-tile bs_tn, once
+                    mbar_expect_tx(bfull, static_cast<uint32_t>(k_total * C::kBBytes));
+                    for (int it = 0; it < k_total; ++it) {
+                        const int tap = it / g.k_chunks;
+                        const int kc = it - tap * g.k_chunks;
+                        tma_load_3d(sB_res + it * C::kBBytes, &g.map_b, bfull, kc * GEMM_BLOCK_K, bs_tn * BN, tap);
+                    }
+                }
+            }
+            for (int wi = first_pair; wi < total_items; wi += pair_stride) {
+                const int sp = BS ? 0 : wi % nsplit;
                 const int pt = wi / nsplit;
                 const int it0 = sp * k_per, it1 = min(k_total, it0 + k_per);
-                const int tn = pt % g.tiles_n;
-                const int tmi = (pt / g.tiles_n) * CG + static_cast<int>(rank);
+                const int tn = BS ? bs_tn : pt % g.tiles_n;
+                const int tmi = BS ? wi : (pt / g.tiles_n) * CG + static_cast<int>(rank);
                 int tm = tmi;
                 int org[GEMM_MAX_RDIMS];
 #pragma unroll
@@ -142,10 +168,18 @@ __global__ void __launch_bounds__(n_threads(GEGLU), 1) gemm_tc_kernel(const __gr
                         const int c3 = org[2] + g.tap_off[tap][2];
                         const int c4 = org[3] + g.tap_off[tap][3];
                         mbar_wait(&empty[stage], phase ^ 1u);
-                        uint8_t* sa = smem + stage * C::kStageBytes;
+                        uint8_t* sa = BS ? sA_ring + stage * kABytes : smem + stage * C::kStageBytes;
                         uint8_t* sb = sa + kABytes;
                         const int k0 = kc * GEMM_BLOCK_K;
-                        if constexpr (CG == 2) {
+                        if constexpr (BS) {
+                            mbar_expect_tx(&full[stage], static_cast<uint32_t>(g.a_tx_bytes));
+                            switch (g.nd) {
+                                case 1: tma_load_2d(sa, &g.map_a, &full[stage], k0, c1); break;
+                                case 2: tma_load_3d(sa, &g.map_a, &full[stage], k0, c1, c2); break;
+                                case 3: tma_load_4d(sa, &g.map_a, &full[stage], k0, c1, c2, c3); break;
+                                default: tma_load_5d(sa, &g.map_a, &full[stage], k0, c1, c2, c3, c4); break;
+                            }
+                        } else if constexpr (CG == 2) {
                             // both CTAs' bytes complete on the LEADER's barrier; only the leader arms it
                             if (leader) mbar_expect_tx(&full[stage], static_cast<uint32_t>(2 * (g.a_tx_bytes + C::kBBytes)));
                             const uint32_t lb = leader_bar_addr(&full[stage]);
@@ -166,7 +200,7 @@ __global__ void __launch_bounds__(n_threads(GEGLU), 1) gemm_tc_kernel(const __gr
                             }
                             tma_load_3d(sb, &g.map_b, &full[stage], k0, tn * BN, tap + bbatch);
                         }
-                        if (++stage == C::kStages) {
+                        if (++stage == nst) {
                             stage = 0;
                             phase ^= 1u;
                         }
@@ -185,8 +219,14 @@ __global__ void __launch_bounds__(n_threads(GEGLU), 1) gemm_tc_kernel(const __gr
         uint32_t phase = 0;
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int wi = first_pair; wi < total_pairs; wi += pair_stride) {
-            const int it0s = (wi % nsplit) * k_per;
+        if constexpr (BS) {
+            if (first_pair < total_items) {
+                mbar_wait(bfull, 0u);
+                tc_fence_after();
+            }
+        }
+        for (int wi = first_pair; wi < total_items; wi += pair_stride) {
+            const int it0s = BS ? 0 : (wi % nsplit) * k_per;
             const int k_iters = min(k_total, it0s + k_per) - it0s;
             mbar_wait(&tempty[acc], acc_phase ^ 1u);      // epilogue(s) have drained this accumulator stage
             tc_fence_after();
@@ -196,9 +236,9 @@ __global__ void __launch_bounds__(n_threads(GEGLU), 1) gemm_tc_kernel(const __gr
                 tc_fence_after();
                 if (lane == 0) {
                     const bool skip_mma = (g.flags & GEMM_DBG_NO_MMA) != 0;
-                    const uint32_t sa = smem_u32(smem + stage * C::kStageBytes);
+                    const uint32_t sa = smem_u32(BS ? sA_ring + stage * kABytes : smem + stage * C::kStageBytes);
                     const uint64_t da = umma_desc_k_sw128(sa);
-                    const uint64_t db = umma_desc_k_sw128(sa + kABytes);
+                    const uint64_t db = umma_desc_k_sw128(BS ? smem_u32(sB_res + it * C::kBBytes) : sa + kABytes);
 #pragma unroll
                     for (int k = 0; k < GEMM_BLOCK_K / 16; ++k) {
                         if (skip_mma) break;
@@ -219,7 +259,7 @@ __global__ void __launch_bounds__(n_threads(GEGLU), 1) gemm_tc_kernel(const __gr
                     }
                 }
                 __syncwarp();
-                if (++stage == C::kStages) {
+                if (++stage == nst) {
                     stage = 0;
                     phase ^= 1u;
                 }
@@ -259,11 +299,11 @@ __global__ void __launch_bounds__(n_threads(GEGLU), 1) gemm_tc_kernel(const __gr
         const uint32_t my_stage = smem_u32(stage_s) + static_cast<uint32_t>(warp - 2) * 2048u;
         const bool bias_staged = GEGLU || ln || ((g.bias != nullptr) && (g.bias_rows == 0));   // GEGLU: always (zeros if no bias)
         const int et = static_cast<int>(threadIdx.x) - 64;       // 0..255 among the epilogue threads
-        for (int wi = first_pair; wi < total_pairs; wi += pair_stride) {
-            const int sp = wi % nsplit;
+        for (int wi = first_pair; wi < total_items; wi += pair_stride) {
+            const int sp = BS ? 0 : wi % nsplit;
             const int pt = wi / nsplit;
-            const int tn = pt % g.tiles_n;
-            const int tmi = (pt / g.tiles_n) * CG + static_cast<int>(rank);
+            const int tn = BS ? bs_tn : pt % g.tiles_n;
+            const int tmi = BS ? wi : (pt / g.tiles_n) * CG + static_cast<int>(rank);
             int tm = tmi;
             // tile row r -> global row
             long long grow = 0;
@@ -590,10 +630,16 @@ int encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dim
 struct Variant {
     int bn, geglu, cg, smem;
     const void* fn;
+    int bs;
 };
+constexpr int kBsSmemBytes = kSmemBudget + 1024 + 256 + 4096 + 256 + 8 * 2048;      // same map as Cfg with the ring at its budget
 template <int BN, bool G, int CG>
 Variant variant() {
-    return Variant{BN, G ? 1 : 0, CG, Cfg<BN, CG>::kSmemBytes, reinterpret_cast<const void*>(&gemm_tc_kernel<BN, G, CG>)};
+    return Variant{BN, G ? 1 : 0, CG, Cfg<BN, CG>::kSmemBytes, reinterpret_cast<const void*>(&gemm_tc_kernel<BN, G, CG>), 0};
+}
+template <int BN, bool G>
+Variant variant_bs() {
+    return Variant{BN, G ? 1 : 0, 1, kBsSmemBytes, reinterpret_cast<const void*>(&gemm_tc_kernel<BN, G, 1, true>), 1};
 }
 const Variant* variants(int* n) {
     static const Variant v[] = {
@@ -601,15 +647,16 @@ const Variant* variants(int* n) {
         variant<256, false, 1>(), variant<64, true, 1>(),   variant<128, true, 1>(),  variant<256, true, 1>(),
         variant<64, false, 2>(),  variant<128, false, 2>(), variant<160, false, 2>(), variant<256, false, 2>(),
         variant<64, true, 2>(),   variant<128, true, 2>(),  variant<256, true, 2>(),
+        variant_bs<160, false>(), variant_bs<128, false>(), variant_bs<128, true>(), variant_bs<64, false>(),
     };
     *n = static_cast<int>(sizeof(v) / sizeof(v[0]));
     return v;
 }
-const Variant* find_variant(int bn, bool geglu, int cg) {
+const Variant* find_variant(int bn, bool geglu, int cg, int bs = 0) {
     int n;
     const Variant* v = variants(&n);
     for (int i = 0; i < n; ++i)
-        if (v[i].bn == bn && v[i].geglu == (geglu ? 1 : 0) && v[i].cg == cg) return &v[i];
+        if (v[i].bn == bn && v[i].geglu == (geglu ? 1 : 0) && v[i].cg == cg && v[i].bs == bs) return &v[i];
     return nullptr;
 }
 
@@ -650,6 +697,29 @@ int tma_encode_f16(CUtensorMap* m, const void* base, int rank, const unsigned lo
         if (i + 1 < rank) st[i] = strides_bytes[i];
     }
     return encode_map(m, base, rank, d, st, bx);
+}
+
+int gemm_bs_bn(long long tiles_m, int N, int K, int ntaps, bool geglu, int num_sms, int force_bn, bool any_k, int* stages_out) {
+    static const bool bs_off = getenv("T2V_NO_BSTAT") != nullptr;
+    static const int bs_kmax = getenv("T2V_BSTAT_KMAX") ? atoi(getenv("T2V_BSTAT_KMAX")) : 5;
+    const int kt = ntaps * ((K + GEMM_BLOCK_K - 1) / GEMM_BLOCK_K);
+    if (bs_off || N <= 16 || (kt > bs_kmax && !any_k)) return 0;
+    const int cands[3] = {160, 128, 64};
+    for (int i = 0; i < 3; ++i) {
+        const int c = cands[i];
+        if (force_bn != 0 && force_bn != c) continue;
+        if (geglu && (c != 128 || (N % c) != 0)) continue;
+        const int tn = (N + c - 1) / c;
+        if (static_cast<double>(N) / (static_cast<double>(tn) * c) < 0.9) continue;
+        const long long b_bytes = static_cast<long long>(kt) * c * GEMM_BLOCK_K * 2;
+        if (b_bytes > kSmemBudget - 4 * kABytes || tn > num_sms) continue;
+        const int stages = static_cast<int>(std::min<long long>(8, (kSmemBudget - b_bytes) / kABytes));
+        const int group = num_sms / tn;                               // CTAs per N-tile
+        if (tiles_m < 3LL * group) continue;                          // too few M-tiles per CTA to amortise the resident load
+        if (stages_out) *stages_out = stages;
+        return c;
+    }
+    return 0;
 }
 
 int gemm_plan(const GemmProblem& p, GemmPlan* plan, int num_sms) {
@@ -739,13 +809,24 @@ int gemm_plan(const GemmProblem& p, GemmPlan* plan, int num_sms) {
             }
         }
     }
+    // ---- B-stationary variant (see the kernel): few K chunks, many M-tiles per CTA
+    plan->bs = 0;
+    if (p.force_bs >= 0 && p.force_cg <= 1 && p.splits <= 1 && p.b_batch_dim < 0) {
+        int stages = 0;
+        const int c = gemm_bs_bn(g.tiles_m, p.N, p.K, p.ntaps, (p.flags & GEMM_GEGLU) != 0, num_sms, p.force_bn, p.force_bs == 1, &stages);
+        if (c > 0) {
+            bn = c;
+            plan->bs = 1;
+            g.bs_stages = stages;
+        }
+    }
     plan->bn = bn;
     // CTA pairs (cta_group::2, M = 256 per pair, each CTA stages half of B).  Measured on B200 (profiles/r01_ncu_gemm.md):
     // no gain over one CTA per tile for this kernel's shapes (69 % vs 66 % tensor-pipe at 24576x2560x1280, slightly slower
     // on the K = 320 layers), so pairs are opt-in (T2V_2CTA=1 or force_cg) until the pair path gets TMA multicast.
     static const bool use_pairs = getenv("T2V_2CTA") != nullptr;
     plan->cg = p.force_cg ? p.force_cg : ((g.tiles_m >= 2 && bn >= 64 && use_pairs) ? 2 : 1);
-    if (bn < 64 || p.b_batch_dim >= 0) plan->cg = 1;     // a pair shares ONE B tile: never across B batches
+    if (bn < 64 || p.b_batch_dim >= 0 || plan->bs) plan->cg = 1;     // a pair shares ONE B tile: never across B batches
     g.tiles_n = (p.N + bn - 1) / bn;
     if ((p.flags & GEMM_GEGLU) && (p.N % bn) != 0) {
         fprintf(stderr, "[t2v_b200] gemm_plan: GEGLU needs N %% BN == 0 (N %d BN %d)\n", p.N, bn);
@@ -821,20 +902,21 @@ int gemm_plan(const GemmProblem& p, GemmPlan* plan, int num_sms) {
             if (r == CUDA_SUCCESS) g.flags |= GEMM_TMA_STORE;
         }
     }
-    const Variant* var = find_variant(bn, (p.flags & GEMM_GEGLU) != 0, plan->cg);
+    const Variant* var = find_variant(bn, (p.flags & GEMM_GEGLU) != 0, plan->cg, plan->bs);
     if (var == nullptr) return -7;
     const int kt = g.ntaps * g.k_chunks;
     g.k_per_split = (kt + g.splits - 1) / g.splits;
     g.splits = (kt + g.k_per_split - 1) / g.k_per_split;      // no empty splits
     const long long pairs = static_cast<long long>((g.tiles_m + plan->cg - 1) / plan->cg) * g.tiles_n * g.splits;
     plan->grid = plan->cg * static_cast<int>(std::min<long long>(pairs, num_sms / plan->cg));
+    if (plan->bs) plan->grid = (num_sms / g.tiles_n) * g.tiles_n;             // equal groups of CTAs per N-tile
     plan->smem = var->smem;
     plan->flops = 2.0 * static_cast<double>(rows) * p.N * p.K * p.ntaps;
     return 0;
 }
 
 int gemm_launch(const GemmPlan& plan, cudaStream_t stream) {
-    const Variant* var = find_variant(plan.bn, (plan.desc.flags & GEMM_GEGLU) != 0, plan.cg);
+    const Variant* var = find_variant(plan.bn, (plan.desc.flags & GEMM_GEGLU) != 0, plan.cg, plan.bs);
     if (var == nullptr) return -1;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));

@@ -30,6 +30,8 @@ enum GemmFlags : int {
     GEMM_DBG_NO_STORE = 256,   // epilogue skips the global stores
     GEMM_DBG_NO_EPI = 512,     // epilogue releases the accumulator without reading it
     GEMM_DBG_NO_MMA = 1024,    // MMA warp commits without issuing tcgen05.mma (pure TMA pipeline)
+    GEMM_DBG_FORCE_BS = 2048,  // t2v_op_gemm only: take the B-stationary variant whenever it is eligible (any K chunk count)
+    GEMM_DBG_NO_BS = 4096,     // t2v_op_gemm only: never take it
 };
 
 struct GemmDesc {
@@ -62,6 +64,7 @@ struct GemmDesc {
     int splits;                      // split-K: work item = (tile, split); each split owns k_per_split k-iterations and
     int k_per_split;                 //   stores its fp32 partial tile at out + split * split_stride (reduced by splitk_reduce)
     long long split_stride;
+    int bs_stages;                   // B-stationary variant: depth of the A-only ring (the weight slice of the N-tile is resident)
 };
 
 struct GemmProblem {
@@ -93,17 +96,23 @@ struct GemmProblem {
     const float* bias32;
     int splits;                      // 0/1 = no split-K; >1: out must be fp32 [splits][rows][ldo], no bias/residual/GEGLU
     long long split_stride;          // elements between split partials
+    int force_bs;                    // 0 = auto, 1 = B-stationary if eligible, -1 = never (tests / A-B runs)
 };
 
 struct GemmPlan {
     GemmDesc desc;
     int bn;
     int cg;                          // 1 = one CTA per tile, 2 = CTA pair (tcgen05 cta_group::2) per two M-tiles
+    int bs;                          // 1 = B-stationary variant (CTA = one N-tile, walks M-tiles; weights resident in smem)
     int grid;
     int smem;
     double flops;
 };
 
+// Tile width the B-stationary variant would use for this problem (0 = not eligible): the model code asks before it packs
+// GEGLU weights, whose interleave depends on the tile width.  tiles_m = ceil(rows / 128) for plain row matrices.
+int gemm_bs_bn(long long tiles_m, int N, int K, int ntaps, bool geglu, int num_sms, int force_bn = 0, bool any_k = false,
+               int* stages_out = nullptr);
 // Builds tensor maps / tile shapes for a problem.  Returns 0 on success.
 int gemm_plan(const GemmProblem& p, GemmPlan* plan, int num_sms);
 int gemm_launch(const GemmPlan& plan, cudaStream_t stream);

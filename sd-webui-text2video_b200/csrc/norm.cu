@@ -6,6 +6,7 @@
 // fp32 math throughout (the reference runs group_norm / layer_norm / SiLU-after-norm in fp32 under autocast and
 // rounds to fp16 only when the value enters the next conv/linear -- exactly where these kernels round).
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -273,6 +274,200 @@ __global__ void __launch_bounds__(kNormThreads) gn_apply_kernel(const __half* __
     }
 }
 
+
+// ---- single-launch GroupNorm: statistics -> per-instance barrier -> normalise (+SiLU) in ONE kernel.
+// grid = (cpi, instances): the `cpi` CTAs of an instance are all co-resident (the host sizes the grid to the machine: no
+// other kernel shares the SMs, every launch of the library is stream-ordered), so they can meet at a sense-reversing barrier
+// in global memory.  When a CTA's row slice fits in shared memory it is kept there between the two passes: the activation
+// is then read ONCE (2 B/elt read + 2 B/elt write instead of 4 + 2) and the second launch with its drain/fill bubble is gone.
+// Deterministic: partials are folded in chunk order in double precision by every CTA of the instance.
+template <bool SILU>
+__global__ void __launch_bounds__(kNormThreads) gn_fused_kernel(const __half* __restrict__ x, long long ldx,
+                                                                __half* __restrict__ y, long long ldy, int C,
+                                                                int rows_per_inst, int rows_per_cta, float eps,
+                                                                float2* __restrict__ partial, unsigned int* __restrict__ count,
+                                                                unsigned int* __restrict__ gen, const __half* __restrict__ gamma,
+                                                                const __half* __restrict__ beta, int cache) {
+    griddep_wait();
+    extern __shared__ __align__(16) float sm[];   // red[2][RL][C] | s_sum[C] | s_sq[C] | fold[8][32][2] doubles | stats[32] float2 | slice
+    const int inst = blockIdx.y;
+    const int chunk = blockIdx.x;
+    const int cpi = gridDim.x;
+    const int C8 = C >> 3;
+    const int cpg = C / kGroups;
+    const RowMap m = row_map(C8);
+    float* red = sm;
+    float* s_sum = sm + 2 * m.RL * C;
+    float* s_sq = s_sum + C;
+    double* fold = reinterpret_cast<double*>(s_sq + C);                 // 8 * 32 * 2 doubles (offset is a multiple of 8 B: C % 8 == 0)
+    float2* st = reinterpret_cast<float2*>(fold + 8 * kGroups * 2);
+    uint4* slice = reinterpret_cast<uint4*>(st + kGroups);              // [rows_per_cta][C8] when `cache`
+    const int r0 = chunk * rows_per_cta;
+    const int r1 = min(r0 + rows_per_cta, rows_per_inst);
+    const __half* base = x + static_cast<long long>(inst) * rows_per_inst * ldx;
+    float s[8], q[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) s[e] = q[e] = 0.f;
+    if (m.active) {
+        constexpr int U = 4;
+        const __half* p = base + static_cast<long long>(r0 + m.rl) * ldx + m.vc * 8;
+        const long long step = static_cast<long long>(m.RL) * ldx;
+        int r = r0 + m.rl;
+        for (; r + (U - 1) * m.RL < r1; r += U * m.RL) {
+            uint4 v[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) v[u] = __ldg(reinterpret_cast<const uint4*>(p + u * step));
+            p += U * step;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (cache) slice[static_cast<size_t>(r - r0 + u * m.RL) * C8 + m.vc] = v[u];
+                const __half2* h2 = reinterpret_cast<const __half2*>(&v[u]);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float2 f = __half22float2(h2[e]);
+                    s[2 * e] += f.x;
+                    q[2 * e] = fmaf(f.x, f.x, q[2 * e]);
+                    s[2 * e + 1] += f.y;
+                    q[2 * e + 1] = fmaf(f.y, f.y, q[2 * e + 1]);
+                }
+            }
+        }
+        for (; r < r1; r += m.RL) {
+            const uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
+            p += step;
+            if (cache) slice[static_cast<size_t>(r - r0) * C8 + m.vc] = v;
+            const __half2* h2 = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float2 f = __half22float2(h2[e]);
+                s[2 * e] += f.x;
+                q[2 * e] = fmaf(f.x, f.x, q[2 * e]);
+                s[2 * e + 1] += f.y;
+                q[2 * e + 1] = fmaf(f.y, f.y, q[2 * e + 1]);
+            }
+        }
+        float4* d0 = reinterpret_cast<float4*>(red + (0 * m.RL + m.rl) * C + m.vc * 8);
+        float4* d1 = reinterpret_cast<float4*>(red + (1 * m.RL + m.rl) * C + m.vc * 8);
+        d0[0] = make_float4(s[0], s[1], s[2], s[3]);
+        d0[1] = make_float4(s[4], s[5], s[6], s[7]);
+        d1[0] = make_float4(q[0], q[1], q[2], q[3]);
+        d1[1] = make_float4(q[4], q[5], q[6], q[7]);
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += kNormThreads) {
+        float a = 0.f, b = 0.f;
+        for (int yy = 0; yy < m.RL; ++yy) {
+            a += red[(0 * m.RL + yy) * C + c];
+            b += red[(1 * m.RL + yy) * C + c];
+        }
+        s_sum[c] = a;
+        s_sq[c] = b;
+    }
+    __syncthreads();
+    if (threadIdx.x < kGroups) {
+        float a = 0.f, b = 0.f;
+        for (int c = 0; c < cpg; ++c) {
+            a += s_sum[threadIdx.x * cpg + c];
+            b += s_sq[threadIdx.x * cpg + c];
+        }
+        partial[(static_cast<long long>(inst) * cpi + chunk) * kGroups + threadIdx.x] = make_float2(a, b);
+    }
+    if (cpi > 1) {
+        // sense-reversing barrier over the CTAs of this instance: every CTA reads the generation BEFORE it arrives; the last
+        // arriver resets the count and bumps the generation.  Bounded spin: a scheduling assumption that ever failed traps
+        // instead of hanging the device.
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned int g0;
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(g0) : "l"(gen + inst) : "memory");
+            __threadfence();
+            const unsigned int prev = atomicAdd(&count[inst], 1u);
+            if (prev == static_cast<unsigned int>(cpi - 1)) {
+                count[inst] = 0u;
+                __threadfence();
+                asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(gen + inst), "r"(g0 + 1u) : "memory");
+            } else {
+                unsigned int g = g0;
+                for (unsigned int spins = 0; g == g0; ++spins) {
+                    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(g) : "l"(gen + inst) : "memory");
+                    if (g == g0) {
+                        __nanosleep(32);
+                        if (spins > (1u << 25)) __trap();
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    } else {
+        __syncthreads();
+    }
+    if (threadIdx.x < 256) {
+        const int gidx = threadIdx.x & 31, part = threadIdx.x >> 5;
+        double a = 0.0, b = 0.0;
+#pragma unroll 4
+        for (int ch = part; ch < cpi; ch += 8) {
+            const float2 pp = __ldcg(&partial[(static_cast<long long>(inst) * cpi + ch) * kGroups + gidx]);
+            a += pp.x;
+            b += pp.y;
+        }
+        fold[(part * kGroups + gidx) * 2 + 0] = a;
+        fold[(part * kGroups + gidx) * 2 + 1] = b;
+    }
+    __syncthreads();
+    if (threadIdx.x < kGroups) {
+        double a = 0.0, b = 0.0;
+#pragma unroll
+        for (int part = 0; part < 8; ++part) {
+            a += fold[(part * kGroups + threadIdx.x) * 2 + 0];
+            b += fold[(part * kGroups + threadIdx.x) * 2 + 1];
+        }
+        const double n = static_cast<double>(rows_per_inst) * cpg;
+        const double mean = a / n;
+        double var = b / n - mean * mean;
+        if (var < 0.0) var = 0.0;
+        st[threadIdx.x] = make_float2(static_cast<float>(mean), static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps))));
+    }
+    __syncthreads();
+    griddep_launch_small();
+    if (!m.active) return;
+    float a[8], b[8];
+    {
+        const uint4 gv = __ldg(reinterpret_cast<const uint4*>(gamma + m.vc * 8));
+        const uint4 bv = __ldg(reinterpret_cast<const uint4*>(beta + m.vc * 8));
+        const __half* gh = reinterpret_cast<const __half*>(&gv);
+        const __half* bh = reinterpret_cast<const __half*>(&bv);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const float2 ms = st[(m.vc * 8 + e) / cpg];
+            a[e] = ms.y * __half2float(gh[e]);
+            b[e] = __half2float(bh[e]) - ms.x * a[e];
+        }
+    }
+    const long long row0 = static_cast<long long>(inst) * rows_per_inst + r0 + m.rl;
+    const __half* px = x + row0 * ldx + m.vc * 8;
+    __half* py = y + row0 * ldy + m.vc * 8;
+    const long long sx = static_cast<long long>(m.RL) * ldx, sy = static_cast<long long>(m.RL) * ldy;
+    constexpr int U = 4;
+    int r = r0 + m.rl;
+    for (; r + (U - 1) * m.RL < r1; r += U * m.RL) {
+        uint4 v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            v[u] = cache ? slice[static_cast<size_t>(r - r0 + u * m.RL) * C8 + m.vc] : __ldg(reinterpret_cast<const uint4*>(px + u * sx));
+        px += U * sx;
+#pragma unroll
+        for (int u = 0; u < U; ++u) *reinterpret_cast<uint4*>(py + u * sy) = gn_apply_vec<SILU>(v[u], a, b);
+        py += U * sy;
+    }
+    for (; r < r1; r += m.RL) {
+        const uint4 v = cache ? slice[static_cast<size_t>(r - r0) * C8 + m.vc] : __ldg(reinterpret_cast<const uint4*>(px));
+        px += sx;
+        *reinterpret_cast<uint4*>(py) = gn_apply_vec<SILU>(v, a, b);
+        py += sy;
+    }
+}
+
 // one warp per row; C <= 2048, C % 8 == 0
 __global__ void __launch_bounds__(256) layernorm_kernel(const __half* __restrict__ x, long long ldx,
                                                         __half* __restrict__ y, long long ldy, long long rows, int C,
@@ -433,8 +628,10 @@ size_t gn_workspace_bytes(int rows_per_inst, int n_inst, int num_sms) {
     const int nchunks = (rows_per_inst + rpc - 1) / rpc;
     // counters (fixed-size region at the START: their location must not depend on the call's shape, they have to
     // stay zero between launches) + stats + partials
+    // (+ the single-launch kernel's partials: up to 2 CTAs per SM in total)
     return kCounterBytes + static_cast<size_t>(n_inst) * kGroups * sizeof(float2) +
-           static_cast<size_t>(n_inst) * nchunks * kGroups * sizeof(float2) + 256;
+           static_cast<size_t>(n_inst) * nchunks * kGroups * sizeof(float2) +
+           (static_cast<size_t>(2 * num_sms) + n_inst) * kGroups * sizeof(float2) + 256;
 }
 
 int groupnorm_silu(const __half* x, long long ldx, __half* y, long long ldy, long long rows, int C, int rows_per_inst,
@@ -449,6 +646,52 @@ int groupnorm_silu(const __half* x, long long ldx, __half* y, long long ldy, lon
     unsigned int* counters = reinterpret_cast<unsigned int*>(ws);
     float2* stats = reinterpret_cast<float2*>(ws + kCounterBytes);
     float2* partial = stats + static_cast<size_t>(n_inst) * kGroups;
+    // ---- single-launch path (phase 0, no cross-rank statistics): all CTAs of the grid must be co-resident
+    static const bool fused_on = getenv("T2V_NO_FUSED_GN") == nullptr;
+    if (phase == 0 && fused_on && (shard == nullptr || shard->peers.nranks <= 1) && n_inst <= 65536) {
+        const size_t inst_bytes = static_cast<size_t>(rows_per_inst) * C * sizeof(__half);
+        const size_t fixed = stats_smem_bytes(C) + 8 * kGroups * 2 * sizeof(double) + kGroups * sizeof(float2);
+        const size_t cache_cap = 200 * 1024 - fixed;                     // slice bytes a lone CTA per SM can keep
+        const int RL = kNormThreads / (C / 8);
+        int cpi = 0, cache = 0;
+        if (n_inst <= num_sms) {
+            const int cmax = num_sms / n_inst;                              // one CTA per SM when caching
+            const long long need = (static_cast<long long>(inst_bytes) + cache_cap - 1) / static_cast<long long>(cache_cap);
+            if (need <= cmax) {
+                cpi = cmax;
+                cache = 1;
+            }
+        }
+        if (!cache && n_inst <= 2 * num_sms && fixed <= 100 * 1024) cpi = (2 * num_sms) / n_inst;      // two lean CTAs per SM, second pass from L2
+        if (cpi > 0) {
+            const int max_useful = (rows_per_inst + RL - 1) / RL;            // at least one row pass per CTA
+            if (cpi > max_useful) cpi = max_useful;
+            if (cpi < 1) cpi = 1;
+            int rpc2 = (rows_per_inst + cpi - 1) / cpi;
+            cpi = (rows_per_inst + rpc2 - 1) / rpc2;
+            size_t smem = fixed + (cache ? static_cast<size_t>(rpc2) * C * sizeof(__half) : 0);
+            if (cache && smem > 226 * 1024) {
+                cache = 0;
+                smem = fixed;
+            }
+            const size_t need_ws = kCounterBytes + static_cast<size_t>(n_inst) * (kGroups + static_cast<size_t>(cpi) * kGroups) * sizeof(float2);
+            (void)need_ws;
+            unsigned int* gen = counters + (kCounterBytes / sizeof(unsigned int)) / 2;
+            static bool attr_done = false;
+            if (!attr_done) {
+                cudaFuncSetAttribute(gn_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+                cudaFuncSetAttribute(gn_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+                attr_done = true;
+            }
+            if (silu)
+                launch_pdl(gn_fused_kernel<true>, dim3(cpi, n_inst), kNormThreads, smem, stream, x, ldx, y, ldy, C, rows_per_inst, rpc2,
+                           eps, partial, counters, gen, gamma, beta, cache);
+            else
+                launch_pdl(gn_fused_kernel<false>, dim3(cpi, n_inst), kNormThreads, smem, stream, x, ldx, y, ldy, C, rows_per_inst, rpc2,
+                           eps, partial, counters, gen, gamma, beta, cache);
+            return cudaGetLastError() == cudaSuccess ? 0 : -2;
+        }
+    }
     GnShard gs;
     memset(&gs, 0, sizeof(gs));
     if (shard != nullptr && shard->peers.nranks > 1) {

@@ -270,9 +270,9 @@ int Builder::gemm(GemmProblem& p) {
         return rc;
     }
     char lab[192];
-    snprintf(lab, sizeof(lab), "gemm rows=%.0f N=%d K=%d taps=%d bn=%d tiles=%dx%d grid=%d%s%s%s", rows, p.N, p.K, p.ntaps, gp.bn,
+    snprintf(lab, sizeof(lab), "gemm rows=%.0f N=%d K=%d taps=%d bn=%d tiles=%dx%d grid=%d%s%s%s%s", rows, p.N, p.K, p.ntaps, gp.bn,
              gp.desc.tiles_m, gp.desc.tiles_n, gp.grid, (p.flags & GEMM_GEGLU) ? " geglu" : "", p.residual ? " +res" : "",
-             gp.desc.splits > 1 ? " splitK" : "");
+             gp.desc.splits > 1 ? " splitK" : "", gp.bs ? " Bstat" : "");
     plan_->steps.push_back(StepRec{[gp](cudaStream_t s) { return gemm_launch(gp, s); }, STEP_GEMM, gp.flops, lab});
     plan_->launches += 1;
     return 0;
@@ -535,17 +535,25 @@ Tok group_norm(NetCtx& c, const Tok& x, const std::string& prefix, long long row
     const int sms = c.b->sms();
     const Tok xx = x;
     char lab[96];
+    if (peers == nullptr) {
+        // one launch: statistics -> per-instance barrier -> normalise(+SiLU) (norm.cu gn_fused_kernel; falls back to the two
+        // kernels below inside groupnorm_silu when the grid cannot be co-resident)
+        snprintf(lab, sizeof(lab), "gn_fused rows=%lld C=%d inst_rows=%lld", x.rows, x.C, rows_per_inst);
+        c.b->step([=](cudaStream_t s) {
+            return groupnorm_silu(xx.p, xx.ld, y.p, y.ld, xx.rows, xx.C, static_cast<int>(rows_per_inst), g, bt, eps, silu ? 1 : 0,
+                                  ws, sms, s, 0);
+        }, 1, STEP_NORM, 0.0, lab);
+        return y;
+    }
     snprintf(lab, sizeof(lab), "gn_stats rows=%lld C=%d inst_rows=%lld", x.rows, x.C, rows_per_inst);
     c.b->step([=](cudaStream_t s) {
         GnShard gs;
         memset(&gs, 0, sizeof(gs));
-        if (peers != nullptr) {
-            gs.peers = *peers;          // read at launch: the peer table is filled by t2v_unet_shard_connect
-            gs.slot = slot;
-            gs.total_rows_per_inst = shard_total_rows;
-        }
+        gs.peers = *peers;          // read at launch: the peer table is filled by t2v_unet_shard_connect
+        gs.slot = slot;
+        gs.total_rows_per_inst = shard_total_rows;
         return groupnorm_silu(xx.p, xx.ld, y.p, y.ld, xx.rows, xx.C, static_cast<int>(rows_per_inst), g, bt, eps, silu ? 1 : 0,
-                              ws, sms, s, 1, peers != nullptr ? &gs : nullptr);
+                              ws, sms, s, 1, &gs);
     }, 1, STEP_NORM, 0.0, lab);
     snprintf(lab, sizeof(lab), "gn_apply rows=%lld C=%d inst_rows=%lld", x.rows, x.C, rows_per_inst);
     c.b->step([=](cudaStream_t s) {

@@ -506,7 +506,9 @@ Tok transformer_block(Ctx& c, Tok x, const std::string& p, int heads, long long 
     }
     // feed-forward: GEGLU fused into the first GEMM's epilogue (t2v_model.py:813-821, :833-846)
     const int H = 4 * C;
-    const int bn = (2 * H) % 256 == 0 ? 256 : ((2 * H) % 128 == 0 ? 128 : 64);
+    int bn = (2 * H) % 256 == 0 ? 256 : ((2 * H) % 128 == 0 ? 128 : 64);
+    // K = 320 layers: the B-stationary GEMM variant wants 128-wide GEGLU tiles (the weight interleave follows the tile width)
+    if (const int bs = gemm_bs_bn((R + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M, 2 * H, C, 1, true, c.b->sms())) bn = bs;
     Geglu g = w_geglu(c, p + ".ff.net.0.proj", H, C, bn);
     Tok gg = ln_linear(c, x, p + ".norm3", p + ".ff.net.0.proj#geglu" + std::to_string(bn), g.w, g.b, 2 * H, nullptr, GEMM_GEGLU, bn);
     Tok y = linear(c, gg, prm(c, p + ".ff.net.2.weight"), C, prm(c, p + ".ff.net.2.bias"), &x);

@@ -10,6 +10,7 @@ import torch
 from . import _lib
 
 GEMM_GEGLU = 1
+GEMM_FORCE_BS, GEMM_NO_BS = 2048, 4096      # bring-up switches of t2v_op_gemm: B-stationary variant on / off
 GEMM_OUT_F32 = 2
 
 

@@ -43,7 +43,8 @@ def main():
     plain, shard = make(), make()
     shard.shard_setup()
     out = []
-    shapes = [(2, 24, 32, 32)] if full_model else [(2, 5, 8, 8), (1, 7, 16, 8), (2, 13, 8, 16), (1, world, 8, 8)]
+    # the deepest level (3 downsamples) must keep >= world pixels: 32 x 16 latent -> 4 x 2
+    shapes = [(2, 24, 32, 32)] if full_model else [(2, 9, 32, 16), (1, 11, 16, 32), (2, 13, 32, 16), (1, world, 32, 16)]
     for (B, F, h, w) in shapes:
         g = torch.Generator().manual_seed(B * 100 + F)
         x = torch.randn(B, 4, F, h, w, generator=g)
@@ -79,9 +80,9 @@ def main():
         for sampler, eta in (('DDIM_Gaussian', 0.0), ('DDIM', 0.0), ('UniPC', 0.0), ('DDIM', 0.5)):
             S = 6
             torch.cuda.manual_seed(77)
-            fr_p, lat_p, _ = pp.infer(c, uc, S, 7, 77, 5.0, 64, 64, eta, 'GPU (half precision)', torch.device('cuda'), None, 0, 0.0,
+            fr_p, lat_p, _ = pp.infer(c, uc, S, 9, 77, 5.0, 256, 128, eta, 'GPU (half precision)', torch.device('cuda'), None, 0, 0.0,
                                       None, False, sampler)
-            fr_s, lat_s, _ = ps.infer(c, uc, S, 7, 77, 5.0, 64, 64, eta, 'GPU (half precision)', torch.device('cuda'), None, 0, 0.0,
+            fr_s, lat_s, _ = ps.infer(c, uc, S, 9, 77, 5.0, 256, 128, eta, 'GPU (half precision)', torch.device('cuda'), None, 0, 0.0,
                                       None, False, sampler)
             import numpy as np
             d = np.abs(np.stack(fr_p).astype(int) - np.stack(fr_s).astype(int))

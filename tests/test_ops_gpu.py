@@ -89,6 +89,57 @@ def test_geglu_epilogue(ops, M, K, H, bn, cg):
     assert rel(out, ref) < 4e-3
 
 
+@pytest.mark.parametrize('M,K,N,bias,res', [(24576, 320, 320, True, True), (24576, 320, 960, False, False), (20000, 320, 512, True, False),
+                                            (70000, 64, 64, True, True), (30000, 640, 640, True, True), (19000, 320, 1920, True, False),
+                                            (148 * 3 * 128 // 2 + 5, 320, 320, True, True)])
+def test_linear_b_stationary_variant(ops, M, K, N, bias, res):
+    """The B-stationary GEMM variant (weight slice of the N-tile resident in shared memory, A-only ring) against torch and
+    against the streaming variant: the K order inside the tensor core is the same, so the two must agree bit for bit."""
+    a = torch.randn(M, K, device=dev).half()
+    w = (torch.randn(N, K, device=dev) / K ** 0.5).half()
+    b = torch.randn(N, device=dev).half() if bias else None
+    r = torch.randn(M, N, device=dev).half() if res else None
+    wp = w.view(1, N, K).contiguous()
+    out = ops.gemm(a, wp, N, bias=b, residual=r, flags=ops.GEMM_FORCE_BS)
+    plain = ops.gemm(a, wp, N, bias=b, residual=r, flags=ops.GEMM_NO_BS)
+    ref = a.float() @ w.float().t()
+    if bias:
+        ref = ref + b.float()
+    if res:
+        ref = ref + r.float()
+    assert rel(out, ref) < 2e-3
+    assert torch.equal(out, plain)
+
+
+@pytest.mark.parametrize('M,K,H', [(24576, 320, 1280), (9000, 320, 1280), (40000, 64, 256)])
+def test_geglu_b_stationary_variant(ops, M, K, H):
+    a = torch.randn(M, K, device=dev).half()
+    w = (torch.randn(2 * H, K, device=dev) / K ** 0.5).half()
+    b = torch.randn(2 * H, device=dev).half()
+    wp, bp = ops.pack_geglu_weight(w, b, 128)
+    out = ops.gemm(a, wp, 2 * H, bias=bp, flags=ops.GEMM_GEGLU | ops.GEMM_FORCE_BS, force_bn=128)
+    plain = ops.gemm(a, wp, 2 * H, bias=bp, flags=ops.GEMM_GEGLU | ops.GEMM_NO_BS, force_bn=128)
+    hh = (a.float() @ w.float().t() + b.float()).half()
+    xa, gate = hh.chunk(2, dim=-1)
+    assert rel(out, xa * F.gelu(gate)) < 4e-3
+    assert torch.equal(out, plain)
+
+
+def test_temporal_conv_b_stationary_variant(ops):
+    """3-tap temporal conv (tap = frame offset, zero padding by TMA out-of-bounds fill) through the resident-weight variant."""
+    B, Fr, P, C = 2, 24, 1024, 64
+    x = torch.randn(B, Fr, P, C, device=dev).half()
+    wt = (torch.randn(C, C, 3, 1, 1, device=dev) / (3 * C) ** 0.5).half()
+    wp = ops.pack_conv_weight(wt)
+    taps = ops.conv_taps_temporal()
+    out = ops.gemm(x.view(-1, C), wp, C, dims=[P, Fr, B], taps=taps, flags=ops.GEMM_FORCE_BS)
+    plain = ops.gemm(x.view(-1, C), wp, C, dims=[P, Fr, B], taps=taps, flags=ops.GEMM_NO_BS)
+    xr = x.float().permute(0, 3, 1, 2).reshape(B, C, Fr, P, 1)
+    ref = F.conv3d(xr, wt.float(), padding=(1, 0, 0)).reshape(B, C, Fr, P).permute(0, 2, 3, 1).reshape(-1, C)
+    assert rel(out, ref) < 2e-3
+    assert torch.equal(out, plain)
+
+
 def test_batched_gemm_and_per_sample_bias(ops):
     q = torch.randn(3, 256, 512, device=dev).half()
     k = torch.randn(3, 256, 512, device=dev).half()
@@ -119,6 +170,23 @@ def test_groupnorm_back_to_back_shapes(ops, n_inst, rows, C, silu, eps):
             ref = F.silu(ref)
         ref = ref.permute(0, 2, 1).reshape(-1, C)
         assert rel(y, ref) < 2e-3
+
+
+@pytest.mark.parametrize('n_inst,rows,C', [(48, 256, 640), (2, 6144, 640), (48, 1024, 320), (2, 24576, 320), (48, 16, 1280),
+                                          (300, 16, 128), (24, 4096, 128), (7, 333, 1920), (2, 100, 2560)])
+def test_groupnorm_single_launch_paths(ops, n_inst, rows, C):
+    """The single-launch kernel (statistics -> per-instance barrier -> apply) in its regimes: slice cached in shared memory
+    (one CTA per SM), second pass from L2 (two CTAs per SM), one CTA per instance, and the two-kernel fallback when the
+    instances outnumber the co-resident CTAs; replayed back to back (the barrier's generation counter is reused)."""
+    x = (torch.randn(n_inst * rows, C, device=dev) * 1.5 - 0.25).half()
+    g = (1 + 0.1 * torch.randn(C, device=dev)).half()
+    b = (0.1 * torch.randn(C, device=dev)).half()
+    ref = F.silu(F.group_norm(x.float().view(n_inst, rows, C).permute(0, 2, 1), 32, g.float(), b.float(), 1e-5))
+    ref = ref.permute(0, 2, 1).reshape(-1, C)
+    first = ops.groupnorm(x, g, b, rows, 1e-5, True)
+    assert rel(first, ref) < 2e-3
+    for _ in range(20):
+        assert torch.equal(ops.groupnorm(x, g, b, rows, 1e-5, True), first)       # deterministic fold order, barrier reusable
 
 
 @pytest.mark.parametrize('rows,C', [(1000, 64), (24576, 320), (77, 1280), (5, 512)])
