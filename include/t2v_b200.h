@@ -84,6 +84,22 @@ int t2v_unet_profile(t2v_unet* u, int B, int F, int h, int w, int L, void* strea
 long long t2v_unet_read_tap(t2v_unet* u, const char* name, void* dst, long long cap_elems, void* stream);
 int t2v_unet_enable_taps(t2v_unet* u, int on);
 
+/* ------------------------------------------------------------------------------------------ LoRA hot-merge
+ * replaces StableLoraProcessor.process_lora's weight surgery (stable_lora/stable_utils/lora_processor.py:50-96, :202-246):
+ * instead of re-assigning `m.weight = nn.Parameter(W +- alpha * B @ A)` and re-shipping / re-packing the whole model, the
+ * low-rank update is applied to the library's own copy of ONE weight,
+ *     W <- fp16(W + fp16(fp16(B @ A) * alpha))        (the reference's roundings under autocast; several merges accumulate)
+ * and only the packed variants derived from it (tap-major conv layout, fused q|k|v, GEGLU interleave, LayerNorm-folded
+ * copies) are rebuilt in place -- buffer addresses, plans and captured CUDA graphs stay valid, the next forward just uses the
+ * new weights.  lora_A [rank, cols] and lora_B [out, rank] are fp16 device pointers, cols = in * kernel taps of the weight;
+ * temporal_mean = 1 for Conv3d (3,1,1) weights: lora_A has in * 9 columns, the product is viewed [out, in, 3, 3, 1] and
+ * averaged over the second kernel axis (:86-94).  t2v_unet_lora_clear restores every merged weight from its base copy:
+ * bit-identical to never having merged (the reference's `-=` undo leaves fp16 rounding residue; this does not).        */
+int t2v_unet_lora_merge(t2v_unet* u, const char* weight_name, const void* lora_A, const void* lora_B, int rank, float alpha,
+                        int temporal_mean, void* stream);
+int t2v_unet_lora_clear(t2v_unet* u, void* stream);
+int t2v_unet_lora_merged(t2v_unet* u);          /* number of weights currently carrying a merge */
+
 /* ------------------------------------------------------------------------------------------ frame-sharded clip
  * ONE clip split over the GPUs of a node, one process per GPU (BASELINE config 4: 125 frames over 8 x B200).  Frames are
  * independent inside the spatial modules and coupled in TemporalConvBlock_v2 (t2v_model.py:1201-1212), TemporalTransformer
@@ -149,6 +165,28 @@ int t2v_vae_decode(t2v_vae* v, const void* z, int z_is_f32, float z_scale, void*
 int t2v_vae_encode(t2v_vae* v, const void* x, int x_is_f32, void* moments_out, int N, int H, int W, void* stream);
 double t2v_vae_flops(t2v_vae* v, int nframes, int h, int w);
 
+/* ------------------------------------------------------------------------------------------ text conditioning
+ * replaces FrozenOpenCLIPEmbedder.encode_with_transformer (modelscope/clip_hardcode.py:112-119, :269-274): the OpenCLIP
+ * ViT-H-14 text transformer (token + positional embedding, `layers_run` residual attention blocks with the causal mask --
+ * 23 of the 24 for layer = 'penultimate' -- then ln_final; no text projection).  Parameter names are open_clip's
+ * (`token_embedding.weight`, `positional_embedding`, `transformer.resblocks.N.{ln_1,attn.in_proj_weight,attn.in_proj_bias,
+ * attn.out_proj,ln_2,mlp.c_fc,mlp.c_proj}`, `ln_final`), i.e. the keys of open_clip_pytorch_model.bin without `visual.*`.
+ * Prompt parsing / chunking / emphasis weights stay host Python (clip_hardcode.py:146-395).                      */
+typedef struct t2v_clip t2v_clip;
+typedef struct {
+    int width;          /* 1024 */
+    int heads;          /* 16 (head width must be 64) */
+    int layers_run;     /* 23 = 24 resblocks, 'penultimate' */
+    int context;        /* 77 */
+    int vocab;          /* 49408 */
+} t2v_clip_config;
+int t2v_clip_create(const t2v_clip_config* cfg, t2v_clip** out);
+void t2v_clip_destroy(t2v_clip* m);
+int t2v_clip_set_param(t2v_clip* m, const char* name, const void* data, int dtype, int ndim, const int64_t* shape, void* stream);
+int t2v_clip_param_info(t2v_clip* m, int index, char* name_out, size_t name_cap, int64_t* shape_out, int* ndim_out);
+/* tokens [B, context] int32 (device) -> out [B, context, width] fp16 (out_is_f32 = 0) or fp32: ln_final(transformer(...)) */
+int t2v_clip_encode(t2v_clip* m, const int* tokens, void* out, int out_is_f32, int B, void* stream);
+
 /* ------------------------------------------------------------------------------------------ sampler steps
  * replace the per-step tensor arithmetic of scripts/samplers (ddim/gaussian_sampler.py:125-136,:269-283;
  * ddim/sampler.py:176-218; uni_pc/uni_pc.py:299-307,:378-391,:625-650).                                  */
@@ -159,6 +197,13 @@ int t2v_ddim_step(const float* x, const void* eps_c, const void* eps_u, int eps_
 int t2v_cfg_x0(const float* x, const void* eps_c, const void* eps_u, int eps_is_f32, float* x0, long long n, float g,
                float alpha, float sigma, int cfg_fp16, void* stream);
 int t2v_lincomb(float* out, const float* const* src, const float* coef, int n_src, long long n, void* stream);
+
+/* img2vid inpainting latent of process_modelscope.py:170-219: masked_latents = image_latents * (1 - mask) + latent_noise * mask
+ * with mask[:, :, f] = weights[f] (the per-frame schedule of T2VAnimKeys), evaluated in fp64 like the reference's numpy code.
+ *   image_latents [BC, image_frames, hw] fp32 (image_frames = 1: one encoded image shared by all frames, or F)
+ *   noise, out, mask_out [BC, F, hw] fp64 (mask_out may be NULL); weights [F] fp64 -- all device pointers            */
+int t2v_latent_blend(const float* image_latents, int image_frames, const double* noise, const double* weights, double* out,
+                     double* mask_out, int BC, int F, long long hw, void* stream);
 
 /* ------------------------------------------------------------------------------------------ kernel-level entry
  * points (used by the parity tests; the model-level calls above are built from exactly these launchers).   */

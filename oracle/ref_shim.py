@@ -158,3 +158,24 @@ def load_samplers():
     import importlib
     load_modelscope()
     return importlib.import_module("samplers.samplers_common")
+
+
+def load_key_frames():
+    """The reference's t2v_helpers/key_frames.py with `numexpr` (not installed here) replaced by a stand-in whose
+    `evaluate(expr)` resolves names in the CALLER's frame, which is how numexpr finds `t`, `max_f`, `max_i_f`, `s`
+    (key_frames.py:30-40, :84-88).  pandas is present and used unmodified."""
+    install()
+    import importlib
+    import math
+    import pandas                                            # noqa: F401  imported BEFORE the stand-in exists: pandas probes
+    import pandas.core.computation.expressions               # noqa: F401  for an optional numexpr at import time
+    if "numexpr" not in sys.modules:
+        nx = _mod("numexpr")
+
+        def evaluate(expr):
+            f = sys._getframe(1)
+            env = {k: getattr(math, k) for k in ("sin", "cos", "tan", "exp", "log", "sqrt", "floor", "ceil")}
+            env.update({k: v for k, v in f.f_locals.items() if isinstance(v, (int, float))})
+            return eval(expr, {"__builtins__": {}}, env)          # test infrastructure only: evaluates OUR fixed test strings
+        nx.evaluate = evaluate
+    return importlib.import_module("t2v_helpers.key_frames")

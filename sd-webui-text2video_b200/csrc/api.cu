@@ -113,6 +113,15 @@ int t2v_op_gemm(const void* a, long long lda, int K, int nd, const int* dims, in
     return rc;
 }
 
+int t2v_latent_blend(const float* image_latents, int image_frames, const double* noise, const double* weights, double* out,
+                     double* mask_out, int BC, int F, long long hw, void* stream) {
+    if ((image_frames != 1 && image_frames != F) || BC < 1 || F < 1 || hw < 1) {
+        set_error("latent_blend: image_frames must be 1 or F");
+        return -1;
+    }
+    return latent_blend(image_latents, image_frames, noise, weights, out, mask_out, BC, F, hw, reinterpret_cast<cudaStream_t>(stream));
+}
+
 int t2v_op_pack_conv_weight(const void* src, int src_is_f32, void* dst, int Cout, int Cin, int taps, int n_alloc,
                             int k_alloc, void* stream) {
     return pack_conv_weight(src, src_is_f32, reinterpret_cast<__half*>(dst), Cout, Cin, taps, n_alloc, k_alloc,

@@ -414,6 +414,57 @@ __global__ void cfg_x0_kernel(const float* x, const void* ec, const void* eu, in
     }
 }
 
+// img2vid inpainting latent (process_modelscope.py:209: masked = image_latents * (1 - mask) + latent_noise * mask, numpy
+// float64 with a per-frame mask weight): out[b,c,f,p] = img[b,c,f or 0,p] * (1 - w[f]) + noise[b,c,f,p] * w[f]
+__global__ void latent_blend_kernel(const float* __restrict__ img, int img_frames, const double* __restrict__ noise,
+                                    const double* __restrict__ w, double* __restrict__ out, double* __restrict__ mask, long long n,
+                                    int F, long long hw) {
+    griddep_wait();
+    griddep_launch_small();
+    GRID_STRIDE(i, n) {
+        const long long bc = i / (static_cast<long long>(F) * hw);
+        const long long r = i - bc * F * hw;
+        const int f = static_cast<int>(r / hw);
+        const long long p = r - static_cast<long long>(f) * hw;
+        const double m = w[f];
+        const double a = static_cast<double>(img[(bc * img_frames + (img_frames == 1 ? 0 : f)) * hw + p]);
+        out[i] = __dadd_rn(__dmul_rn(a, __dsub_rn(1.0, m)), __dmul_rn(noise[i], m));
+        if (mask != nullptr) mask[i] = m;
+    }
+}
+
+// LoRA hot-merge (stable_lora/stable_utils/lora_processor.py:50-96 under autocast): the low-rank product is formed with fp32
+// accumulation and rounded to fp16 (torch's autocast matmul), scaled by alpha in fp16, added in fp16.
+__global__ void lora_merge_kernel(__half* __restrict__ w, const __half* __restrict__ A, const __half* __restrict__ B, int out, int cols,
+                                  int rank, float alpha, int temporal_mean) {
+    griddep_wait();
+    griddep_launch_small();
+    const long long n = static_cast<long long>(out) * cols;
+    const int a_cols = temporal_mean ? cols * 3 : cols;
+    GRID_STRIDE(i, n) {
+        const int o = static_cast<int>(i / cols);
+        const int j = static_cast<int>(i - static_cast<long long>(o) * cols);
+        float d;
+        if (temporal_mean) {
+            float sum = 0.f;
+            for (int q = 0; q < 3; ++q) {
+                float acc = 0.f;
+                for (int r = 0; r < rank; ++r)
+                    acc = fmaf(__half2float(B[static_cast<long long>(o) * rank + r]), __half2float(A[static_cast<long long>(r) * a_cols + j * 3 + q]), acc);
+                sum += __half2float(__float2half_rn(acc));
+            }
+            d = __half2float(__float2half_rn(sum / 3.0f));            // torch.mean on fp16: fp32 accumulate, divide, round
+        } else {
+            float acc = 0.f;
+            for (int r = 0; r < rank; ++r)
+                acc = fmaf(__half2float(B[static_cast<long long>(o) * rank + r]), __half2float(A[static_cast<long long>(r) * a_cols + j]), acc);
+            d = __half2float(__float2half_rn(acc));
+        }
+        const float scaled = __half2float(__float2half_rn(d * alpha));
+        w[i] = __float2half_rn(__half2float(w[i]) + scaled);
+    }
+}
+
 inline int ok() { return cudaGetLastError() == cudaSuccess ? 0 : -2; }
 
 }  // namespace
@@ -522,6 +573,20 @@ int lincomb(float* out, const float* const* src, const float* coef, int n_src, l
     launch_pdl(lincomb_kernel, grid_for(n, 256), 256, 0, stream, out, a, n);
     return ok();
 }
+int lora_merge_weight(__half* w, const __half* A, const __half* B, int out, int cols, int rank, float alpha, int temporal_mean,
+                      cudaStream_t stream) {
+    const long long n = static_cast<long long>(out) * cols;
+    launch_pdl(lora_merge_kernel, grid_for(n, 256), 256, 0, stream, w, A, B, out, cols, rank, alpha, temporal_mean);
+    return ok();
+}
+
+int latent_blend(const float* img, int img_frames, const double* noise, const double* w, double* out, double* mask, int BC, int F,
+                 long long hw, cudaStream_t stream) {
+    const long long n = static_cast<long long>(BC) * F * hw;
+    launch_pdl(latent_blend_kernel, grid_for(n, 256), 256, 0, stream, img, img_frames, noise, w, out, mask, n, F, hw);
+    return ok();
+}
+
 int cfg_x0(const float* x, const void* eps_c, const void* eps_u, int eps_is_f32, float* x0, long long n, float g,
            float alpha, float sigma, int cfg_fp16, cudaStream_t stream) {
     launch_pdl(cfg_x0_kernel, grid_for(n, 256), 256, 0, stream, x, eps_c, eps_u, eps_is_f32, x0, n, g, alpha, sigma, cfg_fp16);

@@ -27,6 +27,15 @@ namespace {
 #ifndef T2V_GEGLU_EW
 #define T2V_GEGLU_EW 8
 #endif
+// Epilogue latency hiding for the generic (non-GEGLU) path, both measured on B200 (profiles/r02_gemm_epilogue.md):
+//   T2V_EPI_PIPE   : the tcgen05.ld of the NEXT column chunk is in flight while the current chunk is converted and stored
+//   T2V_EPI_STAGE2 : two TMA-store staging buffers per epilogue warp (the store of chunk i reads its buffer while chunk i+1 is staged)
+#ifndef T2V_EPI_PIPE
+#define T2V_EPI_PIPE 1
+#endif
+#ifndef T2V_EPI_STAGE2
+#define T2V_EPI_STAGE2 1
+#endif
 constexpr int epi_warps(bool geglu) { return geglu ? T2V_GEGLU_EW : 8; }
 constexpr int n_threads(bool geglu) { return 64 + 32 * epi_warps(geglu); }
 constexpr int kABytes = GEMM_BLOCK_M * GEMM_BLOCK_K * 2;   // 16 KB
@@ -37,9 +46,12 @@ struct Cfg {
     static constexpr int kBBytes = (BN / CG) * GEMM_BLOCK_K * 2;      // a CTA of a pair stages half of the B tile
     static constexpr int kStageBytes = kABytes + kBBytes;
     static constexpr int kStages = (kSmemBudget / kStageBytes) > 8 ? 8 : (kSmemBudget / kStageBytes);
-    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + 4096 /*bias + colsum tiles*/ +
+    static constexpr int kBaseBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + 4096 /*bias + colsum tiles*/ +
                                       256 /*pad to 512*/ + 8 * 2048 /*TMA-store staging, one 32x32 fp16 chunk per epilogue warp*/;
+    static constexpr bool kStage2 = T2V_EPI_STAGE2 != 0 && kBaseBytes + 8 * 2048 <= 227 * 1024;     // second staging bank where it fits
+    static constexpr int kSmemBytes = kBaseBytes + (kStage2 ? 8 * 2048 : 0);
 };
+constexpr int kBsRing = kSmemBudget - (T2V_EPI_STAGE2 ? 8 * 2048 : 0);      // B-stationary: resident weights + A ring live below this offset
 
 // erf-form GELU x * Phi(x) (F.gelu default, t2v_model.py:821).  Phi(x) = 1/2 erfc(-x / sqrt 2); for z = |x| / sqrt 2
 // erfc(z) = t (a1 + t (a2 + t (a3 + t (a4 + t a5)))) exp(-z^2), t = 1 / (1 + p z) (Abramowitz-Stegun 7.1.26, |error| <=
@@ -73,7 +85,8 @@ __global__ void __launch_bounds__(n_threads(GEGLU), 1) gemm_tc_kernel(const __gr
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);      // SWIZZLE_128B atoms need 1024 B alignment
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (BS ? kSmemBudget : C::kStages * C::kStageBytes));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (BS ? kBsRing : C::kStages * C::kStageBytes));
+    constexpr bool kStage2 = BS ? (T2V_EPI_STAGE2 != 0) : C::kStage2;
     uint64_t* full = bars;                       // [kStages] TMA -> MMA
     uint64_t* empty = bars + kBarStages;         // [kStages] MMA -> TMA
     uint64_t* tfull = bars + 2 * kBarStages;     // [2] MMA -> epilogue
@@ -296,7 +309,8 @@ __global__ void __launch_bounds__(n_threads(GEGLU), 1) gemm_tc_kernel(const __gr
         // accumulator); per-sample bias rows (time-embedding add of the ResBlock convs) are read per thread.
         const bool ln = (g.flags & GEMM_LN) != 0;
         const bool tma_st = !GEGLU && (g.flags & GEMM_TMA_STORE) != 0 && EW == 8;
-        const uint32_t my_stage = smem_u32(stage_s) + static_cast<uint32_t>(warp - 2) * 2048u;
+        const uint32_t my_stage0 = smem_u32(stage_s) + static_cast<uint32_t>(warp - 2) * 2048u;
+        uint32_t stage_bank = 0;                       // kStage2: alternates between the two staging banks (16 KB apart)
         const bool bias_staged = GEGLU || ln || ((g.bias != nullptr) && (g.bias_rows == 0));   // GEGLU: always (zeros if no bias)
         const int et = static_cast<int>(threadIdx.x) - 64;       // 0..255 among the epilogue threads
         for (int wi = first_pair; wi < total_items; wi += pair_stride) {
@@ -382,13 +396,31 @@ __global__ void __launch_bounds__(n_threads(GEGLU), 1) gemm_tc_kernel(const __gr
                 asm volatile("bar.sync 1, %0;" ::"n"(32 * EW) : "memory");     // epilogue warps only (named barrier 1)
             }
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * 256);
+            constexpr bool kPipe = !GEGLU && T2V_EPI_PIPE != 0;
+            uint32_t un[CW];                           // kPipe: accumulator chunk in flight (loaded one iteration ahead)
+            if constexpr (kPipe) {
+                if (hsel < nchunks && !(g.flags & GEMM_DBG_NO_EPI)) {
+                    if constexpr (CW == 32) tmem_ld_32x32(taddr + hsel * CW, un);
+                    else tmem_ld_32x16(taddr + hsel * CW, un);
+                }
+            }
             for (int ci = hsel; ci < nchunks; ci += CSTEP) {
                 if (g.flags & GEMM_DBG_NO_EPI) break;
                 const int c0 = ci * CW;
                 uint32_t u[CW];
                 uint32_t ug[CW];
-                if constexpr (CW == 32) tmem_ld_32x32(taddr + c0, u);
-                else tmem_ld_32x16(taddr + c0, u);
+                if constexpr (kPipe) {
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < CW; ++j) u[j] = un[j];
+                    if (ci + CSTEP < nchunks) {
+                        if constexpr (CW == 32) tmem_ld_32x32(taddr + (ci + CSTEP) * CW, un);
+                        else tmem_ld_32x16(taddr + (ci + CSTEP) * CW, un);
+                    }
+                } else {
+                    if constexpr (CW == 32) tmem_ld_32x32(taddr + c0, u);
+                    else tmem_ld_32x16(taddr + c0, u);
+                }
                 if (geglu) {
                     if constexpr (CW == 32) tmem_ld_32x32(taddr + BN / 2 + c0, ug);
                     else tmem_ld_32x16(taddr + BN / 2 + c0, ug);
@@ -452,7 +484,7 @@ __global__ void __launch_bounds__(n_threads(GEGLU), 1) gemm_tc_kernel(const __gr
                         bv[j] = (bias != nullptr && pcol + j < g.N) ? __half2float(__ldg(bias + pcol + j)) : 0.f;
                     }
                 }
-                tmem_ld_wait();
+                if constexpr (!kPipe) tmem_ld_wait();
                 float v[CW];
                 if (ln) {
 #pragma unroll
@@ -479,7 +511,13 @@ __global__ void __launch_bounds__(n_threads(GEGLU), 1) gemm_tc_kernel(const __gr
                             }
                         }
                     }
-                    if (lane == 0) bulk_wait_read0();              // the previous chunk's store has finished READING the buffer
+                    const uint32_t my_stage = my_stage0 + (kStage2 ? stage_bank * 16384u : 0u);
+                    if constexpr (kStage2) {
+                        if (lane == 0) bulk_wait_read1();          // the store before the previous one has finished READING this bank
+                        stage_bank ^= 1u;
+                    } else {
+                        if (lane == 0) bulk_wait_read0();          // the previous chunk's store has finished READING the buffer
+                    }
                     __syncwarp();
                     const uint32_t rowb = my_stage + static_cast<uint32_t>(lane) * 64u;
                     const int sw = (lane >> 1) & 3;                // SWIZZLE_64B: 16-byte chunk ^= address bits [7,9)
@@ -632,7 +670,7 @@ struct Variant {
     const void* fn;
     int bs;
 };
-constexpr int kBsSmemBytes = kSmemBudget + 1024 + 256 + 4096 + 256 + 8 * 2048;      // same map as Cfg with the ring at its budget
+constexpr int kBsSmemBytes = kBsRing + 1024 + 256 + 4096 + 256 + 8 * 2048 * (T2V_EPI_STAGE2 ? 2 : 1);   // Cfg's map, ring at its budget
 template <int BN, bool G, int CG>
 Variant variant() {
     return Variant{BN, G ? 1 : 0, CG, Cfg<BN, CG>::kSmemBytes, reinterpret_cast<const void*>(&gemm_tc_kernel<BN, G, CG>), 0};
@@ -712,8 +750,10 @@ int gemm_bs_bn(long long tiles_m, int N, int K, int ntaps, bool geglu, int num_s
         const int tn = (N + c - 1) / c;
         if (static_cast<double>(N) / (static_cast<double>(tn) * c) < 0.9) continue;
         const long long b_bytes = static_cast<long long>(kt) * c * GEMM_BLOCK_K * 2;
-        if (b_bytes > kSmemBudget - 4 * kABytes || tn > num_sms) continue;
-        const int stages = static_cast<int>(std::min<long long>(8, (kSmemBudget - b_bytes) / kABytes));
+        if (geglu) continue;      // measured: the GEGLU epilogue (MUFU / issue bound) gains nothing from resident weights and loses
+                                  // with the 128-wide tiles they need (512 vs 678 TFLOP/s on the level-0 feed-forward)
+        if (b_bytes > kBsRing - 4 * kABytes || tn > num_sms) continue;
+        const int stages = static_cast<int>(std::min<long long>(8, (kBsRing - b_bytes) / kABytes));
         const int group = num_sms / tn;                               // CTAs per N-tile
         if (tiles_m < 3LL * group) continue;                          // too few M-tiles per CTA to amortise the resident load
         if (stages_out) *stages_out = stages;

@@ -105,6 +105,11 @@ int pack_conv_weight(const void* src, int src_is_f32, __half* dst, int Cout, int
 int pack_geglu_weight(const void* w, const void* b, int src_is_f32, __half* wdst, __half* bdst, int H, int K, int bn,
                       cudaStream_t stream);
 int convert_to_f16(const void* src, int src_is_f32, __half* dst, long long n, cudaStream_t stream);
+// LoRA merge into a weight in its PyTorch layout [out, cols] (cols = in * kernel taps):
+//   w[o, j] = fp16(w[o, j] + fp16(fp16(sum_r B[o, r] A[r, j]) * alpha))                                   (temporal_mean = 0)
+//   w[o, i, kt] += alpha * mean_j fp16(sum_r B[o, r] A[r, (i * 3 + kt) * 3 + j]), j = 0..2, same roundings   (temporal_mean = 1, cols = in * 3)
+int lora_merge_weight(__half* w, const __half* A, const __half* B, int out, int cols, int rank, float alpha, int temporal_mean,
+                      cudaStream_t stream);
 // LayerNorm folded into a Linear: wout[n,k] = fp16(w[n,k] * gamma[k]); colsum[n] = sum_k wout[n,k];
 // bias32[n] = sum_k w[n,k] * beta[k] (+ bias[n])
 int fold_ln_into_linear(const __half* w, const __half* bias, const __half* gamma, const __half* beta, __half* wout,
@@ -114,6 +119,11 @@ int fold_ln_into_linear(const __half* w, const __half* bias, const __half* gamma
 int splitk_reduce(const float* part, int splits, long long split_stride, long long rows, int N, const __half* bias,
                   int bias_rows, long long bias_stride, const __half* residual, long long ldr, __half* out, long long ldo,
                   cudaStream_t stream);
+
+// img2vid inpainting latents: out = img * (1 - w[f]) + noise * w[f] in fp64 (the reference blends in numpy float64,
+// process_modelscope.py:199-209); img [BC, img_frames (1 or F), hw] fp32, noise / out / mask [BC, F, hw] fp64, w [F] fp64
+int latent_blend(const float* img, int img_frames, const double* noise, const double* w, double* out, double* mask, int BC, int F,
+                 long long hw, cudaStream_t stream);
 
 // sampler updates (fp32 latents [B,C,F,h,w]; eps from the UNet in fp16, cond / uncond)
 struct DdimStepParams {

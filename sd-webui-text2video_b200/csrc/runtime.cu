@@ -10,9 +10,93 @@ namespace t2v {
 
 // ----------------------------------------------------------------------------------------- ParamStore
 ParamStore::~ParamStore() {
-    for (auto& kv : params_)
+    for (auto& kv : params_) {
         if (kv.second.data) cudaFree(kv.second.data);
+        if (kv.second.base) cudaFree(kv.second.base);
+    }
     invalidate_packed();
+}
+
+void ParamStore::add_recipe(const std::string& key, std::vector<std::string> sources, std::function<int(cudaStream_t)> run) {
+    recipes_.push_back(PackRecipe{key, std::move(sources), std::move(run)});
+}
+
+std::string ParamStore::key_of(const void* p) const {
+    if (p == nullptr) return "";
+    for (auto& kv : params_)
+        if (kv.second.data == p) return kv.first;
+    for (auto& kv : packed_)
+        if (kv.second == p) return kv.first;
+    return "";
+}
+
+int ParamStore::repack(const std::vector<std::string>& dirty_in, cudaStream_t s) {
+    std::set<std::string> dirty(dirty_in.begin(), dirty_in.end());
+    for (auto& r : recipes_) {              // creation order = dependency order (a folded weight is created after its source pack)
+        bool hit = false;
+        for (auto& src : r.sources)
+            if (dirty.count(src)) hit = true;
+        if (!hit) continue;
+        const int rc = r.run(s);
+        if (rc != 0) {
+            set_error("re-packing '%s' failed (%d)", r.key.c_str(), rc);
+            return rc;
+        }
+        dirty.insert(r.key);
+    }
+    return 0;
+}
+
+int ParamStore::lora_merge(const std::string& name, const __half* A, const __half* B, int rank, float alpha, int temporal_mean,
+                           cudaStream_t s) {
+    auto it = params_.find(name);
+    if (it == params_.end() || !it->second.set) {
+        set_error("lora_merge: parameter '%s' is not loaded", name.c_str());
+        return -1;
+    }
+    Param& p = it->second;
+    if (p.shape.size() < 2 || rank < 1) {
+        set_error("lora_merge: '%s' is not a matrix / conv weight", name.c_str());
+        return -2;
+    }
+    const int out = static_cast<int>(p.shape[0]);
+    const int cols = static_cast<int>(p.elems / out);
+    if (temporal_mean && !(p.shape.size() == 5 && p.shape[2] == 3 && p.shape[3] == 1 && p.shape[4] == 1)) {
+        set_error("lora_merge: temporal_mean needs a Conv3d (3,1,1) weight, '%s' is not", name.c_str());
+        return -2;
+    }
+    if (p.base == nullptr) {
+        const size_t bytes = ((p.elems + 7) / 8 * 8) * sizeof(__half);
+        if (cudaMalloc(&p.base, bytes) != cudaSuccess) {
+            set_error("lora_merge: cudaMalloc of the base copy of '%s' failed", name.c_str());
+            return -3;
+        }
+        cudaMemcpyAsync(p.base, p.data, bytes, cudaMemcpyDeviceToDevice, s);
+    }
+    int rc = lora_merge_weight(p.data, A, B, out, cols, rank, alpha, temporal_mean, s);
+    if (rc != 0) return rc;
+    return repack({name}, s);
+}
+
+int ParamStore::lora_clear(cudaStream_t s) {
+    std::vector<std::string> dirty;
+    for (auto& kv : params_) {
+        Param& p = kv.second;
+        if (p.base == nullptr) continue;
+        cudaMemcpyAsync(p.data, p.base, ((p.elems + 7) / 8 * 8) * sizeof(__half), cudaMemcpyDeviceToDevice, s);
+        cudaStreamSynchronize(s);
+        cudaFree(p.base);
+        p.base = nullptr;
+        dirty.push_back(kv.first);
+    }
+    return dirty.empty() ? 0 : repack(dirty, s);
+}
+
+int ParamStore::merged_count() const {
+    int n = 0;
+    for (auto& kv : params_)
+        if (kv.second.base != nullptr) ++n;
+    return n;
 }
 
 void ParamStore::expect(const std::string& name, std::vector<long long> shape) {
@@ -63,6 +147,11 @@ int ParamStore::set(const std::string& name, const void* src, int dtype, int ndi
     } else {
         int rc = convert_to_f16(src, dtype, p.data, p.elems, s);
         if (rc != 0) return rc;
+    }
+    if (p.base != nullptr) {      // a re-shipped weight replaces base + merges alike
+        cudaStreamSynchronize(s);
+        cudaFree(p.base);
+        p.base = nullptr;
     }
     p.set = true;
     ++version_;
@@ -124,6 +213,7 @@ __half* ParamStore::new_packed(const std::string& key, long long elems) {
 void ParamStore::invalidate_packed() {
     for (auto& kv : packed_) cudaFree(kv.second);
     packed_.clear();
+    recipes_.clear();
 }
 
 // ----------------------------------------------------------------------------------------- Arena
@@ -393,7 +483,10 @@ const __half* w_conv(NetCtx& c, const std::string& name, int taps, int n_alloc, 
     if (__half* p = P.packed(key)) return p;
     if (c.b->dry()) return nullptr;
     __half* dst = P.new_packed(key, static_cast<long long>(taps) * n_alloc * k_alloc);
-    if (!dst || pack_conv_weight(prm.data, 0, dst, cout, cin, taps, n_alloc, k_alloc, c.stream) != 0) c.b->error = -11;
+    const __half* src = prm.data;
+    auto recipe = [=](cudaStream_t s) { return pack_conv_weight(src, 0, dst, cout, cin, taps, n_alloc, k_alloc, s); };
+    if (!dst || recipe(c.stream) != 0) c.b->error = -11;
+    P.add_recipe(key, {name}, recipe);
     return dst;
 }
 // stride-2 conv weight [Cout, Cin, 3, 3] -> [1][Cout][9*Cin] with K index = tap*Cin + c (matches im2col_s2 columns)
@@ -413,14 +506,21 @@ const __half* w_conv_kmajor(NetCtx& c, const std::string& name) {
     // pack_conv_weight source index = (o*Cin + k)*taps + tap ; we want dst[o][tap*Cin + k] -> do it tap by tap
     __half* dst = P.new_packed(key, static_cast<long long>(cout) * 9 * cin);
     __half* tmp = P.new_packed(key + "#tmp", static_cast<long long>(9) * cout * cin);
-    if (!dst || !tmp || pack_conv_weight(prm.data, 0, tmp, cout, cin, 9, cout, cin, c.stream) != 0) {
+    const __half* src = prm.data;
+    auto recipe = [=](cudaStream_t s) {
+        const int rc = pack_conv_weight(src, 0, tmp, cout, cin, 9, cout, cin, s);
+        if (rc != 0) return rc;
+        for (int tap = 0; tap < 9; ++tap)
+            cudaMemcpy2DAsync(dst + static_cast<long long>(tap) * cin, static_cast<size_t>(9) * cin * 2,
+                              tmp + static_cast<long long>(tap) * cout * cin, static_cast<size_t>(cin) * 2,
+                              static_cast<size_t>(cin) * 2, cout, cudaMemcpyDeviceToDevice, s);
+        return 0;
+    };
+    if (!dst || !tmp || recipe(c.stream) != 0) {
         c.b->error = -11;
         return dst;
     }
-    for (int tap = 0; tap < 9; ++tap)
-        cudaMemcpy2DAsync(dst + static_cast<long long>(tap) * cin, static_cast<size_t>(9) * cin * 2,
-                          tmp + static_cast<long long>(tap) * cout * cin, static_cast<size_t>(cin) * 2,
-                          static_cast<size_t>(cin) * 2, cout, cudaMemcpyDeviceToDevice, c.stream);
+    P.add_recipe(key, {name}, recipe);
     return dst;
 }
 // concatenated bias-free projections (q|k|v or k|v) -> one [sum N, K] matrix
@@ -445,12 +545,21 @@ const __half* w_cat(NetCtx& c, const std::vector<std::string>& names) {
         c.b->error = -11;
         return nullptr;
     }
-    long long off = 0;
+    std::vector<std::pair<const __half*, long long>> parts;
     for (auto& n : names) {
         const Param& prm = P.get(n);
-        cudaMemcpyAsync(dst + off, prm.data, prm.elems * sizeof(__half), cudaMemcpyDeviceToDevice, c.stream);
-        off += prm.elems;
+        parts.push_back({prm.data, prm.elems});
     }
+    auto recipe = [=](cudaStream_t s) {
+        long long off = 0;
+        for (auto& pr : parts) {
+            cudaMemcpyAsync(dst + off, pr.first, pr.second * sizeof(__half), cudaMemcpyDeviceToDevice, s);
+            off += pr.second;
+        }
+        return 0;
+    };
+    recipe(c.stream);
+    P.add_recipe(key, names, recipe);
     return dst;
 }
 Geglu w_geglu(NetCtx& c, const std::string& prefix, int H, int K, int bn) {
@@ -472,7 +581,12 @@ Geglu w_geglu(NetCtx& c, const std::string& prefix, int H, int K, int bn) {
     if (c.b->dry()) return g;
     __half* wd = P.new_packed(key, static_cast<long long>(2) * H * K);
     __half* bd = P.new_packed(key + "#b", static_cast<long long>(2) * H);
-    if (!wd || !bd || pack_geglu_weight(w.data, bb.data, 0, wd, bd, H, K, bn, c.stream) != 0) c.b->error = -11;
+    const __half* ws = w.data;
+    const __half* bs = bb.data;
+    auto recipe = [=](cudaStream_t s) { return pack_geglu_weight(ws, bs, 0, wd, bd, H, K, bn, s); };
+    if (!wd || !bd || recipe(c.stream) != 0) c.b->error = -11;
+    P.add_recipe(key, {prefix + ".weight", prefix + ".bias"}, recipe);
+    P.add_recipe(key + "#b", {key}, [](cudaStream_t) { return 0; });       // the packed bias travels with the packed weight
     g.w = wd;
     g.b = bd;
     return g;
@@ -589,10 +703,15 @@ Tok ln_linear(NetCtx& c, const Tok& x, const std::string& ln_prefix, const std::
             w = P.new_packed(k, static_cast<long long>(N) * K);
             __half* csh = P.new_packed(k + "#cs", 2LL * N);        // fp32 arrays live in the same cache (2 halves each)
             __half* bsh = P.new_packed(k + "#b32", 2LL * N);
-            if (!w || !csh || !bsh ||
-                fold_ln_into_linear(w_src, bias_src, prm(c, ln_prefix + ".weight"), prm(c, ln_prefix + ".bias"), w,
-                                    reinterpret_cast<float*>(csh), reinterpret_cast<float*>(bsh), N, K, c.stream) != 0)
-                c.b->error = -12;
+            const __half* gam = prm(c, ln_prefix + ".weight");
+            const __half* bet = prm(c, ln_prefix + ".bias");
+            __half* wdst = w;
+            auto recipe = [=](cudaStream_t s) {
+                return fold_ln_into_linear(w_src, bias_src, gam, bet, wdst, reinterpret_cast<float*>(csh), reinterpret_cast<float*>(bsh),
+                                           N, K, s);
+            };
+            if (!w || !csh || !bsh || recipe(c.stream) != 0) c.b->error = -12;
+            P.add_recipe(k, {ln_prefix + ".weight", ln_prefix + ".bias", P.key_of(w_src), P.key_of(bias_src)}, recipe);
         }
         wf = w;
         cs = reinterpret_cast<const float*>(P.packed(k + "#cs"));

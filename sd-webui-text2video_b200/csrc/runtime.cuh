@@ -13,6 +13,7 @@
 #include <functional>
 #include <map>
 #include <memory>
+#include <set>
 #include <string>
 #include <vector>
 
@@ -21,10 +22,19 @@ namespace t2v {
 // ----------------------------------------------------------------------------------------- parameters
 struct Param {
     std::vector<long long> shape;
-    __half* data = nullptr;      // fp16 copy in the ORIGINAL (PyTorch) layout, library-owned
+    __half* data = nullptr;      // fp16 copy in the ORIGINAL (PyTorch) layout, library-owned (the EFFECTIVE weight: base + merged LoRAs)
+    __half* base = nullptr;      // copy of the shipped weight, kept from the first LoRA merge on (lora_clear restores it bit for bit)
     long long elems = 0;
     bool expected = false;
     bool set = false;
+};
+
+// How one packed variant is (re)built from its sources: replayed in creation order when a source changes WITHOUT a new
+// weights version (LoRA hot-merge), so packed buffers keep their addresses and every plan / captured graph stays valid.
+struct PackRecipe {
+    std::string key;
+    std::vector<std::string> sources;      // parameter names and / or keys of other packed variants
+    std::function<int(cudaStream_t)> run;
 };
 
 class ParamStore {
@@ -41,10 +51,22 @@ public:
     __half* new_packed(const std::string& key, long long elems);
     void invalidate_packed();
     unsigned long long version() const { return version_; }
+    // packed-variant recipes (see PackRecipe) and the name a device pointer is known under ("" if unknown)
+    void add_recipe(const std::string& key, std::vector<std::string> sources, std::function<int(cudaStream_t)> run);
+    std::string key_of(const void* p) const;
+    // LoRA hot-merge (stable_lora/stable_utils/lora_processor.py:50-96): data = fp16(data + fp16(fp16(B @ A) * alpha)), then only
+    // the packed variants that depend on `name` are rebuilt in place.  temporal_mean: Conv3d (3,1,1) weights, the product is
+    // viewed [out, in, 3, 3, 1] and averaged over the second kernel axis (:86-94).
+    int lora_merge(const std::string& name, const __half* lora_A, const __half* lora_B, int rank, float alpha, int temporal_mean,
+                   cudaStream_t s);
+    int lora_clear(cudaStream_t s);          // every merged weight back to its base copy (bit-identical to never merging)
+    int merged_count() const;
 
 private:
+    int repack(const std::vector<std::string>& dirty, cudaStream_t s);
     std::map<std::string, Param> params_;
     std::map<std::string, __half*> packed_;
+    std::vector<PackRecipe> recipes_;
     unsigned long long version_ = 0;
 };
 

@@ -1296,6 +1296,17 @@ int t2v_unet_shard_info(t2v_unet* u, int F, int* frame_begin, int* frame_end, in
     return 0;
 }
 
+// ------------------------------------------------------------------------------------------ LoRA hot-merge
+int t2v_unet_lora_merge(t2v_unet* u, const char* weight_name, const void* lora_A, const void* lora_B, int rank, float alpha,
+                        int temporal_mean, void* stream) {
+    return u->params.lora_merge(weight_name, reinterpret_cast<const __half*>(lora_A), reinterpret_cast<const __half*>(lora_B), rank,
+                                alpha, temporal_mean, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int t2v_unet_lora_clear(t2v_unet* u, void* stream) { return u->params.lora_clear(reinterpret_cast<cudaStream_t>(stream)); }
+
+int t2v_unet_lora_merged(t2v_unet* u) { return u->params.merged_count(); }
+
 int t2v_unet_enable_taps(t2v_unet* u, int on) {
     u->taps_enabled = on != 0;
     return 0;

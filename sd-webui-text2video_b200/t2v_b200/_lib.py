@@ -29,6 +29,9 @@ SIGNATURES = {
     't2v_unet_profile': (c_int, [P, c_int, c_int, c_int, c_int, c_int, P, C.POINTER(c_double)]),
     't2v_unet_read_tap': (c_ll, [P, c_char_p, P, c_ll, P]),
     't2v_unet_enable_taps': (c_int, [P, c_int]),
+    't2v_unet_lora_merge': (c_int, [P, c_char_p, P, P, c_int, c_float, c_int, P]),
+    't2v_unet_lora_clear': (c_int, [P, P]),
+    't2v_unet_lora_merged': (c_int, [P]),
     't2v_unet_shard_setup': (c_int, [P, c_int, c_int]),
     't2v_unet_shard_prepare': (c_int, [P, c_int, c_int, c_int, c_int, c_int, P, P]),
     't2v_unet_shard_connect': (c_int, [P, c_int, c_int, c_int, c_int, c_int, P, P]),
@@ -43,10 +46,16 @@ SIGNATURES = {
     't2v_vae_decode': (c_int, [P, P, c_int, c_float, P, c_int, c_int, c_int, c_int, c_int, P]),
     't2v_vae_encode': (c_int, [P, P, c_int, P, c_int, c_int, c_int, P]),
     't2v_vae_flops': (c_double, [P, c_int, c_int, c_int]),
+    't2v_clip_create': (c_int, [P, C.POINTER(P)]),
+    't2v_clip_destroy': (None, [P]),
+    't2v_clip_set_param': (c_int, [P, c_char_p, P, c_int, c_int, C.POINTER(C.c_int64), P]),
+    't2v_clip_param_info': (c_int, [P, c_int, c_char_p, C.c_size_t, C.POINTER(C.c_int64), C.POINTER(c_int)]),
+    't2v_clip_encode': (c_int, [P, P, P, c_int, c_int, P]),
     't2v_ddim_step': (c_int, [P, P, P, c_int, P, c_ll, c_ll, c_int, c_int, c_float, c_int, c_float, c_float, c_float, c_float,
                               c_float, P, c_int, P]),
     't2v_cfg_x0': (c_int, [P, P, P, c_int, P, c_ll, c_float, c_float, c_float, c_int, P]),
     't2v_lincomb': (c_int, [P, C.POINTER(P), C.POINTER(c_float), c_int, c_ll, P]),
+    't2v_latent_blend': (c_int, [P, c_int, P, P, P, P, c_int, c_int, c_ll, P]),
     't2v_op_gemm': (c_int, [P, c_ll, c_int, c_int, C.POINTER(c_int), c_int, C.POINTER(c_int), P, c_int, c_int, c_int,
                             c_int, P, c_ll, P, c_int, c_ll, P, c_ll, c_float, c_int, c_int, P]),
     't2v_op_pack_conv_weight': (c_int, [P, c_int, P, c_int, c_int, c_int, c_int, c_int, P]),
@@ -77,6 +86,10 @@ class ShardExportC(C.Structure):
     """t2v_shard_export (include/t2v_b200.h): what the ranks of a frame-sharded clip swap once per shape."""
     _fields_ = [('comm_handle', C.c_ubyte * 64), ('slab_handle', C.c_ubyte * 64), ('rank', c_int), ('nranks', c_int),
                 ('n_exchanges', c_int), ('n_groupnorms', c_int), ('dst_offset', c_ll * 192)]
+
+
+class ClipConfigC(C.Structure):
+    _fields_ = [('width', c_int), ('heads', c_int), ('layers_run', c_int), ('context', c_int), ('vocab', c_int)]
 
 
 class VAEConfigC(C.Structure):

@@ -210,6 +210,28 @@ class UNetSD(_NativeModule):
             else:
                 self.register_buffer(name, f32(val))
 
+    # -- LoRA hot-merge on the library's packed weights (include/t2v_b200.h "LoRA hot-merge"; t2v_b200/lora.py drives it)
+    def lora_merge(self, weight_name, lora_A, lora_B, alpha, temporal_mean=False):
+        """W <- W + alpha * B @ A for ONE weight of the state_dict, on the device, with the reference's fp16 roundings; the
+        nn.Parameter held by this mirror keeps the base value (lora_clear() returns the library to it exactly)."""
+        self.sync_weights()
+        A = lora_A.to('cuda', torch.float16).reshape(lora_A.shape[0], -1).contiguous()
+        B = lora_B.to('cuda', torch.float16).reshape(lora_B.shape[0], -1).contiguous()
+        if B.shape[1] != A.shape[0]:
+            raise ValueError(f'LoRA rank mismatch for {weight_name}: A {tuple(A.shape)} B {tuple(B.shape)}')
+        p = dict(self.named_parameters())[weight_name]
+        cols = p.numel() // p.shape[0]
+        if B.shape[0] != p.shape[0] or A.shape[1] != (cols * 3 if temporal_mean else cols):
+            raise ValueError(f'LoRA shapes do not fit {weight_name} {tuple(p.shape)}: A {tuple(A.shape)} B {tuple(B.shape)}')
+        _lib.check(_lib.lib().t2v_unet_lora_merge(self._handle, weight_name.encode(), _lib.ptr(A), _lib.ptr(B), A.shape[0], float(alpha),
+                                                  int(temporal_mean), _lib.stream_ptr()), f'lora_merge({weight_name})')
+
+    def lora_clear(self):
+        _lib.check(_lib.lib().t2v_unet_lora_clear(self._handle, _lib.stream_ptr()), 'lora_clear')
+
+    def lora_merged(self):
+        return _lib.load_library().t2v_unet_lora_merged(self._handle)
+
     # -- frame-sharded clip (include/t2v_b200.h "frame-sharded clip"; t2v_b200/distributed.py drives it)
     def shard_setup(self, group=None):
         """Makes this module one rank of a frame-sharded denoiser: ONE clip split over the ranks of `group` (default: the

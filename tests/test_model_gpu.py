@@ -321,3 +321,60 @@ def test_vae_encode_vs_reference_fixture_and_compute_latents(gold_dir):
     # decode(encode(x)) runs end to end (round trip through both plans)
     rec = ae.decode(post.mode())
     assert rec.shape == (2, 3, 64, 96) and torch.isfinite(rec).all()
+
+
+# ---------------------------------------------------------------------------------------- LoRA hot-merge
+def test_lora_hot_merge_matches_reference_arithmetic_and_unmerges_bit_exactly(tiny):
+    """StableLoraProcessor.process_lora (stable_lora/stable_utils/lora_processor.py:50-96, :202-246) on the library's packed
+    weights: Linear inside the fused q|k|v + LayerNorm-folded copy, the GEGLU projection, a 3x3 conv (tap-major pack), a
+    temporal Conv3d (product averaged over the second kernel axis) and a 1x1 projection.  Gate: the hot-merged forward equals
+    the forward of a second module whose weights were merged with torch (the reference's ops, fp16) and shipped normally;
+    lora_clear() gives back the pre-merge output bit for bit without rebuilding the plan."""
+    from t2v_b200.modules import UNetSD
+    from t2v_b200.lora import StableLoraProcessor
+    cfg, W, Wh, net = tiny
+    g = torch.Generator().manual_seed(21)
+    x = torch.randn(2, 4, 3, 8, 8, generator=g).cuda()
+    y = torch.randn(2, 77, 1024, generator=g).cuda()
+    t = torch.tensor([400, 30]).cuda()
+    before = net(x, t, y).clone()
+    launches = net.num_launches()
+    names = ['input_blocks.1.1.transformer_blocks.0.attn1.to_q', 'input_blocks.1.1.transformer_blocks.0.attn2.to_k',
+             'input_blocks.1.1.transformer_blocks.0.ff.net.0.proj', 'input_blocks.1.0.in_layers.2',
+             'input_blocks.1.0.temopral_conv.conv1.2', 'input_blocks.1.1.proj_in', 'middle_block.1.proj_out']
+    mods = dict(net.named_modules())
+    rank, alpha = 4, 0.75
+    lora, merged_w = {}, {}
+    for n in names:
+        w = mods[n].weight.detach()
+        out_c = w.shape[0]
+        cols = w.numel() // out_c
+        temporal = w.dim() == 5
+        A = (torch.randn(rank, cols * 3 if temporal else cols, generator=g) * 0.2).half().cuda()
+        B = (torch.randn(out_c, rank, generator=g) * 0.2).half().cuda()
+        lora[n + '.lora_A'], lora[n + '.lora_B'] = A, B
+        prod = (B @ A)                                                       # fp16 matmul, fp32 accumulate: autocast's B @ A
+        if temporal:
+            prod = prod.view(out_c, w.shape[1], 3, 3, 1).mean(dim=-2, keepdim=True)
+        merged_w[n + '.weight'] = (w.half() + prod.view(w.shape).half() * alpha)      # process_lora_weight (:50-58), fp16
+    n_merged = StableLoraProcessor().process_lora(net, [lora], lora_alpha=alpha)
+    assert n_merged == len(names) and net.lora_merged() == len(names)
+    hot = net(x, t, y).clone()
+    assert not torch.equal(hot, before)
+    assert net.num_launches() == launches                                    # same plan, same graph
+    ref_net = UNetSD(dim=64).half()
+    sd = {k: v.clone() for k, v in W.items()}
+    for k, v in merged_w.items():
+        sd[k] = v.float().cpu()
+    ref_net.load_state_dict(sd, strict=True)
+    ref_net = ref_net.cuda().eval()
+    ref = ref_net(x, t, y)
+    e = errs(hot, ref)
+    report('lora_hot_merge_vs_torch_merge', max=e[0], rms=e[1], equal_frac=(hot == ref).float().mean().item())
+    assert e[1] < 5e-4, e                                                    # identical up to rare 1-ulp differences of B @ A's summation order
+    # a second merge accumulates on top of the first, like two LoRA files
+    net.lora_merge(names[0] + '.weight', lora[names[0] + '.lora_A'], lora[names[0] + '.lora_B'], 0.5)
+    assert not torch.equal(net(x, t, y), hot)
+    StableLoraProcessor().process_lora(net, [], undo_merge=True)
+    assert net.lora_merged() == 0
+    assert torch.equal(net(x, t, y), before)                                 # bit-identical to never merging

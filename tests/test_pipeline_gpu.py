@@ -102,9 +102,20 @@ def test_process_modelscope_entry_point(pipe):
     pm.pipe = pipe[0]
     c, uc = conds()
     outs = pm.process_modelscope({'prompt_embeds': c, 'n_prompt_embeds': uc, 'steps': 3, 'frames': 2, 'seed': 5, 'cfg_scale': 4.0,
-                                  'width': 64, 'height': 64, 'batch_count': 2, 'sampler': 'DDIM_Gaussian'})
+                                  'width': 64, 'height': 64, 'batch_count': 2, 'sampler': 'DDIM_Gaussian', 'return_frames': True})
     assert len(outs) == 2 and len(outs[0]) == 2 and outs[0][0].shape == (64, 64, 3)
     assert not np.array_equal(outs[0][0], outs[1][0])           # batch i uses seed + i
+    # default return type = the reference's: a list of data-URL videos (process_modelscope.py:34, :256-262)
+    urls = pm.process_modelscope({'prompt_embeds': c, 'n_prompt_embeds': uc, 'steps': 3, 'frames': 2, 'seed': 5, 'cfg_scale': 4.0,
+                                  'width': 64, 'height': 64, 'batch_count': 1, 'sampler': 'DDIM_Gaussian'})
+    assert len(urls) == 1 and isinstance(urls[0], str) and urls[0].startswith('data:video/') and ';base64,' in urls[0]
+    if urls[0].startswith('data:video/avi'):                   # no ffmpeg on the box: uncompressed AVI, frames recoverable bit for bit
+        import base64
+        raw = base64.b64decode(urls[0].split(',', 1)[1])
+        assert raw[:4] == b'RIFF' and raw[8:12] == b'AVI '
+        first = raw.index(b'00db') + 8
+        got = np.frombuffer(raw[first:first + 64 * 64 * 3], dtype=np.uint8).reshape(64, 64, 3)[::-1]
+        assert np.array_equal(got, outs[0][0])
     with pytest.raises(RuntimeError):
         pipe[0].infer('a cat', '', 3, 2, 1, 3.0, 64, 64)        # string prompts need a clip_encoder
     with pytest.raises(RuntimeError):
@@ -126,11 +137,38 @@ def test_vid2vid_through_the_entry_point(pipe, sampler):
     lat = p.compute_latents(vid, 'GPU (half precision)', torch.device('cuda'))
     assert lat.shape == (1, 4, 3, 8, 8) and lat.dtype == torch.float32 and not lat.is_cuda and torch.isfinite(lat).all()
     base = dict(prompt_embeds=c, n_prompt_embeds=uc, steps=6, frames=3, seed=11, cfg_scale=5.0, width=64, height=64,
-                sampler=sampler)
+                sampler=sampler, return_frames=True)
     out = pm.process_modelscope(dict(base, do_vid2vid=True, vid2vid_frames_tensor=vid, strength=0.5))
     txt = pm.process_modelscope(dict(base))
     assert len(out) == 1 and len(out[0]) == 3 and out[0][0].shape == (64, 64, 3)
     assert any((a != b).any() for a, b in zip(out[0], txt[0]))          # the input video steers the result
     with pytest.raises(NotImplementedError):
         pm.process_modelscope(dict(base, do_vid2vid=True))                # no frames given: file reading is webui plumbing
+    pm.pipe = None
+
+
+def test_img2vid_inpainting_latents_and_entry_point(pipe):
+    """img2vid (process_modelscope.py:170-219): per-frame weights from the key-frame schedule, the fp64 blend
+    image_latents * (1 - mask) + noise * mask on the device vs numpy, and the run through the entry point."""
+    from t2v_b200 import process_modelscope as pm
+    p = pipe[0]
+    Wenc = UO.make_weights(VO.encoder_param_specs(VO.VAEConfig()), seed=5)
+    p.autoencoder.load_state_dict(Wenc, strict=False)
+    p.autoencoder.cuda()
+    pm.pipe = p
+    c, uc = conds()
+    img = torch.rand((3, 64, 64), generator=torch.Generator().manual_seed(8)) * 2 - 1
+    F_, n_i = 5, 3
+    noise = np.random.RandomState(3).normal(size=(1, 4, F_, 8, 8))
+    lat, mask = pm.inpainting_latents(p, img, F_, 64, 64, n_i, '0:(t/max_i_f), "max_i_f":(1)', 7, 'GPU (half precision)', noise)
+    il = p.compute_latents(img.view(1, 3, 1, 64, 64), 'GPU (half precision)', torch.device('cuda')).numpy()      # [1,4,1,8,8]
+    w = np.array([0.0, 0.5, 1.0, 1.0, 1.0]).reshape(1, 1, F_, 1, 1)
+    ref = il * (1 - w) + noise * w                                           # numpy float64, as the reference
+    assert lat.dtype == torch.float64 and np.array_equal(lat.cpu().numpy(), ref)
+    assert np.array_equal(mask.cpu().numpy(), np.broadcast_to(w, ref.shape))
+    base = dict(prompt_embeds=c, n_prompt_embeds=uc, steps=4, frames=F_, seed=11, cfg_scale=5.0, width=64, height=64,
+                sampler='DDIM_Gaussian', return_frames=True)
+    out = pm.process_modelscope(dict(base, inpainting_frames=n_i, inpainting_image_tensor=img, inpainting_noise=noise))
+    txt = pm.process_modelscope(dict(base))
+    assert len(out[0]) == F_ and any((a != b).any() for a, b in zip(out[0], txt[0]))
     pm.pipe = None
