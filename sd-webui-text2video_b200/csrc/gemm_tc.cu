@@ -27,14 +27,16 @@ namespace {
 #ifndef T2V_GEGLU_EW
 #define T2V_GEGLU_EW 8
 #endif
-// Epilogue latency hiding for the generic (non-GEGLU) path, both measured on B200 (profiles/r02_gemm_epilogue.md):
+// Epilogue latency-hiding experiments for the generic (non-GEGLU) path, build-time switches.  Both measured on B200
+// (profiles/r02_gemm_epilogue_ab.txt): neither moves the K = 320 layers nor the forward (23.00 / 23.26 / 23.06 / 23.27 ms for
+// 00 / 10 / 01 / 11, run-to-run noise +-0.15 ms), so they are OFF by default:
 //   T2V_EPI_PIPE   : the tcgen05.ld of the NEXT column chunk is in flight while the current chunk is converted and stored
 //   T2V_EPI_STAGE2 : two TMA-store staging buffers per epilogue warp (the store of chunk i reads its buffer while chunk i+1 is staged)
 #ifndef T2V_EPI_PIPE
-#define T2V_EPI_PIPE 1
+#define T2V_EPI_PIPE 0
 #endif
 #ifndef T2V_EPI_STAGE2
-#define T2V_EPI_STAGE2 1
+#define T2V_EPI_STAGE2 0
 #endif
 constexpr int epi_warps(bool geglu) { return geglu ? T2V_GEGLU_EW : 8; }
 constexpr int n_threads(bool geglu) { return 64 + 32 * epi_warps(geglu); }
@@ -739,7 +741,10 @@ int tma_encode_f16(CUtensorMap* m, const void* base, int rank, const unsigned lo
 
 int gemm_bs_bn(long long tiles_m, int N, int K, int ntaps, bool geglu, int num_sms, int force_bn, bool any_k, int* stages_out) {
     static const bool bs_off = getenv("T2V_NO_BSTAT") != nullptr;
-    static const int bs_kmax = getenv("T2V_BSTAT_KMAX") ? atoi(getenv("T2V_BSTAT_KMAX")) : 5;
+    // measured on B200 (profiles/r02_gemm_epilogue_ab.txt): bit-identical results, no gain on the K = 320 layers (33.5 vs 33.6 us
+    // +res, 23.2 vs 24.4 us without) nor on the forward (23.27 vs 23.35 ms) -- those layers are not bound by the operand stream
+    // after all.  Kept as an opt-in (T2V_BSTAT_KMAX=<max K chunks>, e.g. 5) and for the op-level tests (GEMM_DBG_FORCE_BS).
+    static const int bs_kmax = getenv("T2V_BSTAT_KMAX") ? atoi(getenv("T2V_BSTAT_KMAX")) : 0;
     const int kt = ntaps * ((K + GEMM_BLOCK_K - 1) / GEMM_BLOCK_K);
     if (bs_off || N <= 16 || (kt > bs_kmax && !any_k)) return 0;
     const int cands[3] = {160, 128, 64};
