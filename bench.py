@@ -42,9 +42,10 @@ def parse():
     ap.add_argument('--denoise-steps', type=int, default=50)
     ap.add_argument('--sampler', default='DDIM_Gaussian')
     ap.add_argument('--cfg-scale', type=float, default=17.0)
-    ap.add_argument('--mode', default='sample_dp', choices=['sample_dp', 'frame_shard'],
+    ap.add_argument('--mode', default='sample_dp', choices=['sample_dp', 'frame_shard', 'frame_shard_cfg'],
                     help='N>1: sample_dp = one clip per GPU (weak scaling, the default the driver runs); frame_shard = ONE clip '
-                         'split over the N GPUs by frames (strong scaling, BASELINE config 4: --frames 125)')
+                         'split over the N GPUs by frames (strong scaling, BASELINE config 4: --frames 125); frame_shard_cfg = the same '
+                         'with the guidance pair split as well: N/2 frame shards x (cond | uncond), one eps exchange per step')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-gpu-baseline', action='store_true', help='skip the torch-eager GPU comparator leg of the N=1 run')
     ap.add_argument('--cpu-frames', type=int, default=0, help='frames of the CPU sample (0 = the metric\'s F)')
@@ -276,8 +277,16 @@ def run_b200(args):
     pipe = TextToVideoSynthesis(None, device=dev)
     randomize_(pipe.sd_model, seed=0)
     randomize_(pipe.autoencoder, seed=3)
-    frame_shard = args.mode == 'frame_shard' and world > 1
-    fs = pipe.enable_frame_shard() if frame_shard else None
+    frame_shard = args.mode in ('frame_shard', 'frame_shard_cfg') and world > 1
+    if args.mode == 'frame_shard_cfg' and world > 1:
+        if world % 2:
+            raise SystemExit('frame_shard_cfg needs an even number of GPUs')
+        os.environ['T2V_CFG_SPLIT'] = '1'                  # even ranks: conditional branch, odd ranks: unconditional (distributed.py)
+        from t2v_b200 import distributed as D0
+        D0.cfg_pair()                                       # collective group creation, same order on every rank
+        fs = pipe.enable_frame_shard(D0.cfg_role_group())
+    else:
+        fs = pipe.enable_frame_shard() if frame_shard else None
     F, H, Wd = args.frames, args.height, args.width
     h, w = H // 8, Wd // 8
     S = args.denoise_steps
@@ -357,7 +366,9 @@ def run_b200(args):
         prof = unet.profile(2, F, h, w, 77) if fs is None else {'gemm': {'ms': 0.0, 'flop': 0.0, 'launches': 0}, 'total_ms': 0.0}
         gemm = prof['gemm']
         achieved = gemm['flop'] / (gemm['ms'] * 1e-3) / 1e12 if gemm['ms'] > 0 else 0.0
-        unet_flops = unet.flops(2, F, h, w, 77) * (world if fs is not None else 1)     # sharded: flops() is this rank's share
+        # sharded: flops() is this rank's share (frame_shard_cfg: B = 1 per rank, half the ranks per branch)
+        unet_flops = (unet.flops(1, F, h, w, 77) * world if args.mode == 'frame_shard_cfg' and fs is not None else
+                      unet.flops(2, F, h, w, 77) * (world if fs is not None else 1))
         vae_flops = pipe.autoencoder.flops(F, h, w)
         clip_flops = S * unet_flops + vae_flops
         launches_clip = S * (unet.num_launches() + 3) + 120
@@ -370,7 +381,8 @@ def run_b200(args):
             'ModelScope architecture, random CLIP-like conditioning)',
             'config': {'workload': f'ModelScope UNetSD {F}f x {H}x{Wd}, {S}-step {args.sampler}, cfg {args.cfg_scale}, batched '
                                    f'cond+uncond forward, + AutoencoderKL decode of {F} frames',
-                       'parallelism': (f'frame-shard x{world}: ONE clip, {F} frames split over the GPUs; activations exchanged inside the UNet '
+                       'parallelism': ((f'CFG split x frame-shard ({world // 2} shards x 2 branches): ' if args.mode == 'frame_shard_cfg' else '') +
+                                       f'frame-shard x{world}: ONE clip, {F} frames split over the GPUs; activations exchanged inside the UNet '
                                        f'kernels over NVLink peer memory ({unet.num_exchanges(F)} layout exchanges per forward, no NCCL call per '
                                        'step), one NCCL all-gather of the final latent before a frame-sharded VAE' if fs is not None else
                                        f'sample-DP x{world} (one clip per GPU, one NCCL all-gather of the decoded clips)' if n_units == world else

@@ -32,6 +32,9 @@ namespace {
 // 00 / 10 / 01 / 11, run-to-run noise +-0.15 ms), so they are OFF by default:
 //   T2V_EPI_PIPE   : the tcgen05.ld of the NEXT column chunk is in flight while the current chunk is converted and stored
 //   T2V_EPI_STAGE2 : two TMA-store staging buffers per epilogue warp (the store of chunk i reads its buffer while chunk i+1 is staged)
+#ifndef T2V_RES_LATE
+#define T2V_RES_LATE 1
+#endif
 #ifndef T2V_EPI_PIPE
 #define T2V_EPI_PIPE 0
 #endif
@@ -471,7 +474,12 @@ __global__ void __launch_bounds__(n_threads(GEGLU), 1) gemm_tc_kernel(const __gr
                 uint4 rcur[NV];
 #pragma unroll
                 for (int k = 0; k < NV; ++k) rcur[k] = rnext[k];
-                if (ci + CSTEP < nchunks) prefetch_res(ci + CSTEP);
+                // ncu (profiles/r02_ncu_gemm_k320.md): fence.proxy.async in the TMA-store path waits for EVERY outstanding generic
+                // memory operation of the thread, so a residual prefetch issued here is paid in full at the fence of this very
+                // chunk (long-scoreboard stall on FENCE.VIEW.ASYNC).  On that path the prefetch of the next chunk is issued
+                // after this chunk's store instead (T2V_RES_LATE); it then overlaps the next chunk's TMEM load.
+                constexpr bool kResLate = T2V_RES_LATE != 0;
+                if (!(kResLate && tma_st) && ci + CSTEP < nchunks) prefetch_res(ci + CSTEP);
                 const int pcol = tn * BN + c0;                    // packed (accumulator) column of v[0]
                 float bv[CW];
                 if (bias_staged) {
@@ -546,6 +554,7 @@ __global__ void __launch_bounds__(n_threads(GEGLU), 1) gemm_tc_kernel(const __gr
                         }
                         bulk_commit();
                     }
+                    if (kResLate && ci + CSTEP < nchunks) prefetch_res(ci + CSTEP);
                 } else
                 if (valid && !(g.flags & GEMM_DBG_NO_STORE)) {
                     if (res_row != nullptr) {

@@ -77,6 +77,20 @@ def exchange_eps(e_mine, group):
     return out[0], out[1]
 
 
+_role_groups = None
+
+
+def cfg_role_group():
+    """CFG split x frame shard (SURVEY.md 8e "2 x 4" layout): the ranks that evaluate the SAME guidance branch form one
+    frame-shard group (even ranks = conditional, odd ranks = unconditional); rank 2i and 2i+1 hold the same frames and
+    exchange their eps once per step (exchange_eps).  Every rank creates both groups (new_group is collective)."""
+    global _role_groups
+    rank, ws = world()
+    if _role_groups is None:
+        _role_groups = [dist.new_group(list(range(r, ws, 2))) for r in (0, 1)]
+    return _role_groups[rank % 2]
+
+
 def pair_shared(noise):
     """Per-step sampler noise in CFG-split mode: both ranks of a pair must apply the IDENTICAL update, but each rank's global
     CUDA generator is its own -- with eta > 0 the latents would silently drift apart after the first step.  Role 0's draw is

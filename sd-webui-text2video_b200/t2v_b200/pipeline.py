@@ -82,6 +82,13 @@ class TextToVideoSynthesis(object):
             own.update(vae_state)                    # decoder-only synthetic states are allowed
             self.autoencoder.load_state_dict(own, strict=True)
         self.autoencoder.eval().half().to(self.device)
+        if clip_encoder is None and model_dir is not None and args.get('ckpt_clip') and \
+                os.path.exists(os.path.join(model_dir, args['ckpt_clip'])):
+            # t2v_pipeline.py:64-69: FrozenOpenCLIPEmbedder(version=<model_dir>/<ckpt_clip>, layer='penultimate'); the text
+            # transformer runs on the library (t2v_b200/clip.py).  Needs a BPE tokenizer for string prompts (open_clip's).
+            from .clip import FrozenOpenCLIPEmbedder
+            clip_encoder = FrozenOpenCLIPEmbedder(version=os.path.join(model_dir, args['ckpt_clip']), layer='penultimate')
+            clip_encoder.model.half().to(self.device)
         self.clip_encoder = clip_encoder
         self.noise_gen = torch.Generator(device='cpu')
         self.last_tensor = None

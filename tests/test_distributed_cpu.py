@@ -143,3 +143,38 @@ def test_frame_shard_host_logic_world3():
         p.join(timeout=30)
     for rank, ok, frames in res:
         assert ok and frames == [0, 2, 4, 6, 8, 10, 12], (rank, ok, frames)
+
+
+def _role_group_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), T2V_CFG_SPLIT='1')
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from t2v_b200 import distributed as D
+    pair, role, pgrp = D.cfg_pair()
+    rgrp = D.cfg_role_group()
+    t = torch.tensor([float(rank)])
+    dist.all_reduce(t, group=pgrp)                   # pair (2i, 2i+1): sum = 4i + 1
+    u = torch.tensor([float(rank)])
+    dist.all_reduce(u, group=rgrp)                   # role group: ranks of the same parity
+    e = torch.full((1, 4, 2, 2, 2), float(rank))
+    ec, eu = D.exchange_eps(e, pgrp)
+    q.put((rank, pair, role, t.item(), u.item(), dist.get_rank(rgrp), dist.get_world_size(rgrp), ec[0, 0, 0, 0, 0].item(), eu[0, 0, 0, 0, 0].item()))
+    dist.destroy_process_group()
+
+
+def test_cfg_split_times_frame_shard_groups_world4():
+    """2 x 2 layout: pairs (0,1), (2,3) exchange eps; role groups {0,2} (cond) and {1,3} (uncond) are the frame-shard groups."""
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_role_group_worker, args=(r, 4, port, q)) for r in range(4)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=30)
+    for rank, pair, role, tsum, usum, rg_rank, rg_ws, ec, eu in res:
+        assert (pair, role) == (rank // 2, rank % 2)
+        assert tsum == 4 * pair + 1 and usum == (2.0 if role == 0 else 4.0)
+        assert (rg_rank, rg_ws) == (rank // 2, 2)
+        assert (ec, eu) == (2.0 * pair, 2.0 * pair + 1)

@@ -362,16 +362,20 @@ def test_lora_hot_merge_matches_reference_arithmetic_and_unmerges_bit_exactly(ti
     hot = net(x, t, y).clone()
     assert not torch.equal(hot, before)
     assert net.num_launches() == launches                                    # same plan, same graph
-    ref_net = UNetSD(dim=64).half()
-    sd = {k: v.clone() for k, v in W.items()}
+    # checker: the fp32 oracle on the torch-merged weights (a 1-ulp difference in one merged weight re-rolls the fp16 rounding
+    # noise of the whole net -- 2e-3 -- so two fp16 forwards cannot be compared more tightly than each against the oracle)
+    sd = {k: v.half().float() for k, v in W.items()}
     for k, v in merged_w.items():
         sd[k] = v.float().cpu()
+    orc = UO.unet_forward(sd, cfg, x.cpu(), t.cpu(), y.cpu().half().float())
+    e_hot, e_before = errs(hot, orc), errs(before, orc)
+    ref_net = UNetSD(dim=64).half()
     ref_net.load_state_dict(sd, strict=True)
     ref_net = ref_net.cuda().eval()
-    ref = ref_net(x, t, y)
-    e = errs(hot, ref)
-    report('lora_hot_merge_vs_torch_merge', max=e[0], rms=e[1], equal_frac=(hot == ref).float().mean().item())
-    assert e[1] < 5e-4, e                                                    # identical up to rare 1-ulp differences of B @ A's summation order
+    e_ref = errs(ref_net(x, t, y), orc)                                      # the same merged weights shipped the ordinary way
+    report('lora_hot_merge', hot_vs_oracle_rms=e_hot[1], shipped_vs_oracle_rms=e_ref[1], unmerged_vs_oracle_rms=e_before[1])
+    assert e_hot[1] < RMS_GATE and e_hot[1] < 1.5 * e_ref[1] + 5e-4, (e_hot, e_ref)
+    assert e_before[1] > 10 * e_hot[1], (e_before, e_hot)                    # the merge really changed the function
     # a second merge accumulates on top of the first, like two LoRA files
     net.lora_merge(names[0] + '.weight', lora[names[0] + '.lora_A'], lora[names[0] + '.lora_B'], 0.5)
     assert not torch.equal(net(x, t, y), hot)
