@@ -24,6 +24,18 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 int num_sms() { return g_num_sms; }
+void clear_pending_error(const char* where) {
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess)
+        fprintf(stderr, "[t2v_b200] %s: clearing a pending CUDA error left by an earlier call: %s (%s)\n", where, cudaGetErrorString(e),
+                cudaGetErrorName(e));
+}
+int launch_status(const char* what) {
+    const cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) return 0;
+    set_error("%s: %s (%s)", what, cudaGetErrorString(e), cudaGetErrorName(e));
+    return -2;
+}
 bool pdl_enabled() {
     static const bool on = getenv("T2V_PDL") != nullptr;      // opt-in: measured 2.7 % SLOWER on the graphed forward
     return on;

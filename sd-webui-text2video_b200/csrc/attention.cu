@@ -217,7 +217,7 @@ int attention(const AttnParams& p, cudaStream_t stream) {
     if (grid.z > 65535 || grid.y > 65535) return -3;
     if (small) launch_pdl(attention_kernel<32>, grid, 64, 0, stream, p);
     else launch_pdl(attention_kernel<64>, grid, 128, 0, stream, p);
-    return cudaGetLastError() == cudaSuccess ? 0 : -2;
+    return launch_status("attention launch");
 }
 
 }  // namespace t2v

@@ -449,7 +449,7 @@ int launch_hd(const AttnParams& p, cudaStream_t stream) {
     dim3 grid(p.batch, p.heads, (p.sq + 63) / 64);
     if (grid.z > 65535 || grid.y > 65535) return -3;
     launch_pdl(attention_hd_kernel<HD>, grid, 128, smem, stream, p);
-    return cudaGetLastError() == cudaSuccess ? 0 : -2;
+    return launch_status("attention_hd launch");
 }
 
 template <int HD, int RT>
@@ -465,7 +465,7 @@ int launch_relpos_rt(const RelposParams& p, cudaStream_t stream) {
     const long long want = (items + RP_WARPS - 1) / RP_WARPS;
     const unsigned grid = static_cast<unsigned>(std::min<long long>(want, static_cast<long long>(num_sms()) * 2));
     launch_pdl(attention_relpos_kernel<HD, RT>, grid, RP_WARPS * 32, SM::kTotal, stream, p);
-    return cudaGetLastError() == cudaSuccess ? 0 : -2;
+    return launch_status("attention_hd launch");
 }
 template <int HD>
 int launch_relpos(const RelposParams& p, cudaStream_t stream) {

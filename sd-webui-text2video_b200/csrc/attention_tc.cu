@@ -387,7 +387,7 @@ int attention_tc_launch(const AttnTcPlan& pl, cudaStream_t stream) {
     a.sl2 = pl.sl2;
     dim3 grid((pl.sq + NT * BQ - 1) / (NT * BQ), pl.heads, pl.batch);
     launch_pdl(attention_tc_kernel, grid, NTHREADS, SMEM_TOTAL, stream, pl.map_q, pl.map_k, pl.map_v, a);
-    return cudaGetLastError() == cudaSuccess ? 0 : -2;
+    return launch_status("attention_tc launch");
 }
 
 }  // namespace t2v

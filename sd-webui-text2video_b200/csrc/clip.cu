@@ -184,7 +184,7 @@ int build(t2v_clip* m, Plan* plan, Arena* arena, bool dry, cudaStream_t stream, 
         bld.step([=](cudaStream_t s) {
             launch_pdl(clip_embed_kernel, dim3(static_cast<unsigned>((R * (W / 8) + 255) / 256)), dim3(256), 0, s, tokens, emb, pos, xx.p,
                        static_cast<int>(R), L, W, vocab);
-            return cudaGetLastError() == cudaSuccess ? 0 : -2;
+            return launch_status("clip launch");
         }, 1, STEP_OTHER, 0.0, "clip embed");
     }
     for (int i = 0; i < cfg.layers_run; ++i) {
@@ -198,7 +198,7 @@ int build(t2v_clip* m, Plan* plan, Arena* arena, bool dry, cudaStream_t stream, 
             const size_t smem = static_cast<size_t>(2) * L * 66 * sizeof(__half);
             bld.step([=](cudaStream_t s) {
                 launch_pdl(clip_attention_kernel, dim3(static_cast<unsigned>(B * heads)), dim3(128), smem, s, q.p, oo.p, L, W, heads);
-                return cudaGetLastError() == cudaSuccess ? 0 : -2;
+                return launch_status("clip launch");
             }, 1, STEP_ATTN, 4.0 * B * heads * static_cast<double>(L) * L * kClipD / 2, "clip causal attention");
         }
         bld.free(qkv);
@@ -213,7 +213,7 @@ int build(t2v_clip* m, Plan* plan, Arena* arena, bool dry, cudaStream_t stream, 
             const long long n8 = R * (4 * W) / 8;
             bld.step([=](cudaStream_t s) {
                 launch_pdl(gelu_kernel, dim3(static_cast<unsigned>((n8 + 255) / 256)), dim3(256), 0, s, hh.p, n8);
-                return cudaGetLastError() == cudaSuccess ? 0 : -2;
+                return launch_status("clip launch");
             }, 1, STEP_OTHER, 0.0, "clip gelu");
         }
         Tok y2 = linear(c, h, prm(c, p + ".mlp.c_proj.weight"), W, prm(c, p + ".mlp.c_proj.bias"), &x);
@@ -323,7 +323,7 @@ int t2v_clip_encode(t2v_clip* m, const int* tokens, void* out, int out_is_f32, i
     }
     const long long n = R * m->cfg.width;
     clip_out_kernel<<<static_cast<unsigned>((n + 255) / 256 > 4096 ? 4096 : (n + 255) / 256), 256, 0, stream>>>(io.second, out, out_is_f32, n);
-    return cudaGetLastError() == cudaSuccess ? 0 : -2;
+    return launch_status("clip launch");
 }
 
 }  // extern "C"

@@ -465,7 +465,7 @@ __global__ void lora_merge_kernel(__half* __restrict__ w, const __half* __restri
     }
 }
 
-inline int ok() { return cudaGetLastError() == cudaSuccess ? 0 : -2; }
+inline int ok() { return launch_status("elementwise launch"); }
 
 }  // namespace
 

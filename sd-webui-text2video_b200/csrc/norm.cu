@@ -689,7 +689,7 @@ int groupnorm_silu(const __half* x, long long ldx, __half* y, long long ldy, lon
             else
                 launch_pdl(gn_fused_kernel<false>, dim3(cpi, n_inst), kNormThreads, smem, stream, x, ldx, y, ldy, C, rows_per_inst, rpc2,
                            eps, partial, counters, gen, gamma, beta, cache);
-            return cudaGetLastError() == cudaSuccess ? 0 : -2;
+            return launch_status("norm launch");
         }
     }
     GnShard gs;
@@ -701,7 +701,7 @@ int groupnorm_silu(const __half* x, long long ldx, __half* y, long long ldy, lon
     if (phase != 2)
         launch_pdl(gn_stats_kernel, dim3(nchunks, n_inst), kNormThreads, stats_smem_bytes(C), stream, x, ldx, C, rows_per_inst,
                    rpc, nchunks, eps, partial, counters, stats, gs);
-    if (phase == 1) return cudaGetLastError() == cudaSuccess ? 0 : -2;
+    if (phase == 1) return launch_status("norm launch");
     // rows per apply block: ~4 blocks per SM overall, at least 4 rows
     long long want_blocks = static_cast<long long>(num_sms) * 4;
     long long per_inst = (want_blocks + n_inst - 1) / n_inst;
@@ -715,7 +715,7 @@ int groupnorm_silu(const __half* x, long long ldx, __half* y, long long ldy, lon
     else
         launch_pdl(gn_apply_kernel<false>, dim3(nblk, n_inst), kNormThreads, 0, stream, x, ldx, y, ldy, C, rows_per_inst,
                    static_cast<int>(rpb), stats, gamma, beta);
-    return cudaGetLastError() == cudaSuccess ? 0 : -2;
+    return launch_status("norm launch");
 }
 
 int layernorm_rowstats(const __half* x, long long ldx, long long rows, int C, float eps, float2* out, cudaStream_t stream) {
@@ -727,7 +727,7 @@ int layernorm_rowstats(const __half* x, long long ldx, long long rows, int C, fl
     else if (nv <= 3) launch_pdl(ln_rowstats_kernel<3>, grid, 256, 0, stream, x, ldx, rows, C, eps, out);
     else if (nv <= 5) launch_pdl(ln_rowstats_kernel<5>, grid, 256, 0, stream, x, ldx, rows, C, eps, out);
     else launch_pdl(ln_rowstats_kernel<8>, grid, 256, 0, stream, x, ldx, rows, C, eps, out);
-    return cudaGetLastError() == cudaSuccess ? 0 : -2;
+    return launch_status("norm launch");
 }
 
 int layernorm(const __half* x, long long ldx, __half* y, long long ldy, long long rows, int C, const __half* gamma,
@@ -735,7 +735,7 @@ int layernorm(const __half* x, long long ldx, __half* y, long long ldy, long lon
     if (C % 8 != 0 || C > 2048) return -1;
     const long long blocks = (rows + 7) / 8;
     launch_pdl(layernorm_kernel, static_cast<unsigned int>(blocks), 256, 0, stream, x, ldx, y, ldy, rows, C, gamma, beta, eps);
-    return cudaGetLastError() == cudaSuccess ? 0 : -2;
+    return launch_status("norm launch");
 }
 
 }  // namespace t2v

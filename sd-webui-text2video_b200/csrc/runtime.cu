@@ -71,7 +71,7 @@ int ParamStore::lora_merge(const std::string& name, const __half* A, const __hal
             set_error("lora_merge: cudaMalloc of the base copy of '%s' failed", name.c_str());
             return -3;
         }
-        cudaMemcpyAsync(p.base, p.data, bytes, cudaMemcpyDeviceToDevice, s);
+        if (cudaMemcpyAsync(p.base, p.data, bytes, cudaMemcpyDeviceToDevice, s) != cudaSuccess) return launch_status("lora_merge base copy");
     }
     int rc = lora_merge_weight(p.data, A, B, out, cols, rank, alpha, temporal_mean, s);
     if (rc != 0) return rc;
@@ -511,9 +511,10 @@ const __half* w_conv_kmajor(NetCtx& c, const std::string& name) {
         const int rc = pack_conv_weight(src, 0, tmp, cout, cin, 9, cout, cin, s);
         if (rc != 0) return rc;
         for (int tap = 0; tap < 9; ++tap)
-            cudaMemcpy2DAsync(dst + static_cast<long long>(tap) * cin, static_cast<size_t>(9) * cin * 2,
-                              tmp + static_cast<long long>(tap) * cout * cin, static_cast<size_t>(cin) * 2,
-                              static_cast<size_t>(cin) * 2, cout, cudaMemcpyDeviceToDevice, s);
+            if (cudaMemcpy2DAsync(dst + static_cast<long long>(tap) * cin, static_cast<size_t>(9) * cin * 2,
+                                  tmp + static_cast<long long>(tap) * cout * cin, static_cast<size_t>(cin) * 2,
+                                  static_cast<size_t>(cin) * 2, cout, cudaMemcpyDeviceToDevice, s) != cudaSuccess)
+                return launch_status("w_conv_kmajor copy");
         return 0;
     };
     if (!dst || !tmp || recipe(c.stream) != 0) {
@@ -553,7 +554,8 @@ const __half* w_cat(NetCtx& c, const std::vector<std::string>& names) {
     auto recipe = [=](cudaStream_t s) {
         long long off = 0;
         for (auto& pr : parts) {
-            cudaMemcpyAsync(dst + off, pr.first, pr.second * sizeof(__half), cudaMemcpyDeviceToDevice, s);
+            if (cudaMemcpyAsync(dst + off, pr.first, pr.second * sizeof(__half), cudaMemcpyDeviceToDevice, s) != cudaSuccess)
+                return launch_status("w_cat copy");
             off += pr.second;
         }
         return 0;

@@ -114,17 +114,17 @@ int shard_exchange(const XchgParams& p, int num_sms, cudaStream_t stream) {
     if (nblk > cap) nblk = cap;
     if (nblk < 1) nblk = 1;
     shard_exchange_kernel<<<static_cast<unsigned>(nblk * nr + 1), kXThreads, 0, stream>>>(p, static_cast<int>(nblk));
-    return cudaGetLastError() == cudaSuccess ? 0 : -2;
+    return launch_status("shard launch");
 }
 
 int shard_bump_epoch(ShardComm* local, cudaStream_t stream) {
     shard_epoch_kernel<<<1, 1, 0, stream>>>(local);
-    return cudaGetLastError() == cudaSuccess ? 0 : -2;
+    return launch_status("shard launch");
 }
 
 int shard_barrier(const ShardPeers& peers, int slot, cudaStream_t stream) {
     shard_barrier_kernel<<<1, 32, 0, stream>>>(peers, slot);
-    return cudaGetLastError() == cudaSuccess ? 0 : -2;
+    return launch_status("shard launch");
 }
 
 }  // namespace t2v

@@ -987,9 +987,9 @@ Plan* get_plan(t2v_unet* u, int B, int F, int h, int w, int L, cudaStream_t stre
             }
             cudaMemsetAsync(u->gn_ws, 0, need, stream);
             u->gn_ws_bytes = need;
-            u->plans.clear();     // plans captured the old pointer
+            for (auto& kv : u->plans) g_io.erase(kv.second.get());     // only THIS denoiser's plans captured the old pointer
+            u->plans.clear();
             u->plan_lru.clear();
-            g_io.clear();
         }
     }
     std::unique_ptr<Plan> plan(new Plan());
@@ -1109,13 +1109,19 @@ int t2v_unet_param_info(t2v_unet* u, int index, char* name_out, size_t name_cap,
 int t2v_unet_forward(t2v_unet* u, const void* x, int x_is_f32, const float* t, const void* ctx, void* out,
                      int out_is_f32, int B, int F, int h, int w, int L, void* stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    clear_pending_error("t2v_unet_forward");
     if (u->cfg.arch == 1 && F > 32) {
         set_error("VideoCrafter temporal attention kernel: at most 32 frames per clip (got %d)", F);
         return -4;
     }
     Plan* plan = get_plan(u, B, F, h, w, L, stream);
     if (!plan) return -1;
-    const IO& io = g_io[plan];
+    auto io_it = g_io.find(plan);
+    if (io_it == g_io.end()) {
+        set_error("internal: plan without I/O staging record");
+        return -6;
+    }
+    const IO& io = io_it->second;
     const t2v_unet_config& cfg = u->cfg;
     const int cin_pad = (cfg.in_dim + 7) / 8 * 8;
     const int F_total = F;
@@ -1299,6 +1305,7 @@ int t2v_unet_shard_info(t2v_unet* u, int F, int* frame_begin, int* frame_end, in
 // ------------------------------------------------------------------------------------------ LoRA hot-merge
 int t2v_unet_lora_merge(t2v_unet* u, const char* weight_name, const void* lora_A, const void* lora_B, int rank, float alpha,
                         int temporal_mean, void* stream) {
+    clear_pending_error("t2v_unet_lora_merge");
     return u->params.lora_merge(weight_name, reinterpret_cast<const __half*>(lora_A), reinterpret_cast<const __half*>(lora_B), rank,
                                 alpha, temporal_mean, reinterpret_cast<cudaStream_t>(stream));
 }

@@ -35,6 +35,13 @@ struct VIO {
     int out_ld;
 };
 std::map<Plan*, VIO> g_vio;
+struct EncIO {
+    __half* x_tok;
+    __half* out_tok;
+    int out_ld;
+    int ho, wo;
+};
+std::map<Plan*, EncIO> g_encio;
 
 void expect_params(t2v_vae* v) {
     ParamStore& P = v->params;
@@ -273,8 +280,10 @@ Plan* get_plan(t2v_vae* v, int frames, int h, int w, cudaStream_t stream) {
             }
             cudaMemsetAsync(v->gn_ws, 0, need, stream);
             v->gn_ws_bytes = need;
+            for (auto& kv : v->plans) g_vio.erase(kv.second.get());          // only THIS handle's plans captured the old pointer
+            for (auto& kv : v->enc_plans) g_encio.erase(kv.second.get());
             v->plans.clear();
-            g_vio.clear();
+            v->enc_plans.clear();
         }
     }
     std::unique_ptr<Plan> plan(new Plan());
@@ -304,13 +313,6 @@ Plan* get_plan(t2v_vae* v, int frames, int h, int w, cudaStream_t stream) {
 // AutoencoderKL.encode up to the moments (t2v_model.py:1640-1644; Encoder.forward autoencoder_modules.py:448-482):
 // frames [N,3,H,W] -> tokens -> conv_in -> per level 2 ResnetBlocks (+ Downsample: pad (0,1,0,1), 3x3 stride 2) -> mid
 // (ResnetBlock, AttnBlock, ResnetBlock) -> GN + swish -> conv_out -> quant_conv 1x1 -> (mean | logvar) tokens.
-struct EncIO {
-    __half* x_tok;
-    __half* out_tok;
-    int out_ld;
-    int ho, wo;
-};
-std::map<Plan*, EncIO> g_encio;
 
 int build_enc(t2v_vae* v, Plan* plan, Arena* arena, bool dry, cudaStream_t stream, int frames, int H, int W, EncIO* io) {
     Builder bld(plan, arena, dry, num_sms());
@@ -405,10 +407,10 @@ Plan* get_enc_plan(t2v_vae* v, int frames, int H, int W, cudaStream_t stream) {
             }
             cudaMemsetAsync(v->gn_ws, 0, need, stream);
             v->gn_ws_bytes = need;
+            for (auto& kv : v->plans) g_vio.erase(kv.second.get());
+            for (auto& kv : v->enc_plans) g_encio.erase(kv.second.get());
             v->plans.clear();
-            g_vio.clear();
             v->enc_plans.clear();
-            g_encio.clear();
         }
     }
     std::unique_ptr<Plan> plan(new Plan());
@@ -502,6 +504,10 @@ int t2v_vae_decode(t2v_vae* v, const void* z, int z_is_f32, float z_scale, void*
     const int frames = B * F;
     Plan* plan = get_plan(v, frames, h, w, stream);
     if (!plan) return -1;
+    if (g_vio.find(plan) == g_vio.end()) {
+        set_error("internal: VAE plan without I/O staging record");
+        return -6;
+    }
     const VIO& io = g_vio[plan];
     const int zpad = (v->cfg.z_channels + 7) / 8 * 8;
     int rc = ingest_latent(z, z_is_f32, io.z_tok, zpad, zpad, B, v->cfg.z_channels, F, h, w, z_scale, stream);
@@ -533,6 +539,10 @@ int t2v_vae_encode(t2v_vae* v, const void* x, int x_is_f32, void* moments_out, i
     }
     Plan* plan = get_enc_plan(v, N, H, W, stream);
     if (!plan) return -1;
+    if (g_encio.find(plan) == g_encio.end()) {
+        set_error("internal: VAE encoder plan without I/O staging record");
+        return -6;
+    }
     const EncIO& io = g_encio[plan];
     int rc = ingest_latent(x, x_is_f32, io.x_tok, 8, 8, N, 3, 1, H, W, 1.0f, stream);
     if (rc != 0) return rc;
