@@ -284,7 +284,9 @@ def run_b200(args):
         os.environ['T2V_CFG_SPLIT'] = '1'                  # even ranks: conditional branch, odd ranks: unconditional (distributed.py)
         from t2v_b200 import distributed as D0
         D0.cfg_pair()                                       # collective group creation, same order on every rank
-        fs = pipe.enable_frame_shard(D0.cfg_role_group())
+        # 2 GPUs: one shard per branch = the plain CFG-pair split (nothing left to shard over frames)
+        fs = pipe.enable_frame_shard(D0.cfg_role_group()) if world > 2 else None
+        frame_shard = fs is not None
     else:
         fs = pipe.enable_frame_shard() if frame_shard else None
     F, H, Wd = args.frames, args.height, args.width

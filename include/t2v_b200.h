@@ -83,6 +83,10 @@ int t2v_unet_profile(t2v_unet* u, int B, int F, int h, int w, int L, void* strea
  * dst receives [(B F), C, h, w] fp16 as the reference module returns it. Returns element count or <0. */
 long long t2v_unet_read_tap(t2v_unet* u, const char* name, void* dst, long long cap_elems, void* stream);
 int t2v_unet_enable_taps(t2v_unet* u, int on);
+/* shape of a tap of the most recent plan: rows x C token matrix viewed as [(rows / (h w)), C, h, w].  A frame-sharded clip
+ * records spatial modules frame-sharded (this rank's frames, full h x w) and temporal modules pixel-sharded (all frames,
+ * h = 1, w = this rank's pixel count).  Returns 0, or -1 if the tap does not exist. */
+int t2v_unet_tap_info(t2v_unet* u, const char* name, long long* rows, int* C, int* h, int* w);
 
 /* ------------------------------------------------------------------------------------------ LoRA hot-merge
  * replaces StableLoraProcessor.process_lora's weight surgery (stable_lora/stable_utils/lora_processor.py:50-96, :202-246):

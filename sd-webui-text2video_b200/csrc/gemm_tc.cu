@@ -41,6 +41,30 @@ namespace {
 #ifndef T2V_EPI_STAGE2
 #define T2V_EPI_STAGE2 0
 #endif
+// In-kernel timeline (build with -DT2V_GEMM_TRACE=1 into a separate library, scripts/gemm_trace.py): two CTAs record clock64
+// stamps of what each role waits for -- producer: ring slot free; MMA: operands landed / accumulator drained / tile committed;
+// two epilogue warps: accumulator ready, chunk loaded, staging buffer free, store issued.  Compiles to nothing by default.
+#ifndef T2V_GEMM_TRACE
+#define T2V_GEMM_TRACE 0
+#endif
+#if T2V_GEMM_TRACE
+constexpr int TRACE_CAP = 4096;
+__device__ unsigned long long* g_trace_buf = nullptr;      // [2 CTAs][4 roles][TRACE_CAP]
+#define TRACE_DECL(role)                                                                                         \
+    unsigned long long* tr_ = nullptr;                                                                           \
+    int tri_ = 0;                                                                                                \
+    {                                                                                                            \
+        const int slot_ = blockIdx.x == 0 ? 0 : (blockIdx.x == gridDim.x / 2 ? 1 : -1);                          \
+        if (g_trace_buf != nullptr && slot_ >= 0 && (role) >= 0) tr_ = g_trace_buf + (slot_ * 4 + (role)) * TRACE_CAP; \
+    }
+#define TRACE(tag)                                                                                               \
+    do {                                                                                                         \
+        if (tr_ != nullptr && tri_ < TRACE_CAP) tr_[tri_++] = (static_cast<unsigned long long>(clock64()) << 8) | static_cast<unsigned long long>(tag); \
+    } while (0)
+#else
+#define TRACE_DECL(role)
+#define TRACE(tag)
+#endif
 constexpr int epi_warps(bool geglu) { return geglu ? T2V_GEGLU_EW : 8; }
 constexpr int n_threads(bool geglu) { return 64 + 32 * epi_warps(geglu); }
 constexpr int kABytes = GEMM_BLOCK_M * GEMM_BLOCK_K * 2;   // 16 KB
@@ -149,6 +173,7 @@ __global__ void __launch_bounds__(n_threads(GEGLU), 1) gemm_tc_kernel(const __gr
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer
         if (lane == 0) {
+            TRACE_DECL(0);
             int stage = 0;
             uint32_t phase = 0;
             if constexpr (BS) {
@@ -186,6 +211,7 @@ __global__ void __launch_bounds__(n_threads(GEGLU), 1) gemm_tc_kernel(const __gr
                         const int c3 = org[2] + g.tap_off[tap][2];
                         const int c4 = org[3] + g.tap_off[tap][3];
                         mbar_wait(&empty[stage], phase ^ 1u);
+                        TRACE(1);
                         uint8_t* sa = BS ? sA_ring + stage * kABytes : smem + stage * C::kStageBytes;
                         uint8_t* sb = sa + kABytes;
                         const int k0 = kc * GEMM_BLOCK_K;
@@ -233,6 +259,7 @@ __global__ void __launch_bounds__(n_threads(GEGLU), 1) gemm_tc_kernel(const __gr
         // ------------------------------------------------------------------ MMA issuer (pair leader only)
         constexpr uint32_t idesc = umma_idesc_f16(GEMM_BLOCK_M * CG, BN);
         if (leader) {
+        TRACE_DECL(lane == 0 ? 1 : -1);
         int stage = 0;
         uint32_t phase = 0;
         int acc = 0;
@@ -246,11 +273,14 @@ __global__ void __launch_bounds__(n_threads(GEGLU), 1) gemm_tc_kernel(const __gr
         for (int wi = first_pair; wi < total_items; wi += pair_stride) {
             const int it0s = BS ? 0 : (wi % nsplit) * k_per;
             const int k_iters = min(k_total, it0s + k_per) - it0s;
+            TRACE(2);
             mbar_wait(&tempty[acc], acc_phase ^ 1u);      // epilogue(s) have drained this accumulator stage
+            TRACE(3);
             tc_fence_after();
             const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * 256);
             for (int it = 0; it < k_iters; ++it) {
                 mbar_wait(&full[stage], phase);
+                TRACE(4);
                 tc_fence_after();
                 if (lane == 0) {
                     const bool skip_mma = (g.flags & GEMM_DBG_NO_MMA) != 0;
@@ -318,6 +348,7 @@ __global__ void __launch_bounds__(n_threads(GEGLU), 1) gemm_tc_kernel(const __gr
         uint32_t stage_bank = 0;                       // kStage2: alternates between the two staging banks (16 KB apart)
         const bool bias_staged = GEGLU || ln || ((g.bias != nullptr) && (g.bias_rows == 0));   // GEGLU: always (zeros if no bias)
         const int et = static_cast<int>(threadIdx.x) - 64;       // 0..255 among the epilogue threads
+        TRACE_DECL(lane == 0 ? (warp == 2 ? 2 : (warp == 6 ? 3 : -1)) : -1);
         for (int wi = first_pair; wi < total_items; wi += pair_stride) {
             const int sp = BS ? 0 : wi % nsplit;
             const int pt = wi / nsplit;
@@ -389,7 +420,9 @@ __global__ void __launch_bounds__(n_threads(GEGLU), 1) gemm_tc_kernel(const __gr
             float2 rs = make_float2(0.f, 1.f);                    // (mean, rstd) of this thread's row
             if (ln && valid) rs = __ldg(g.rowstat + grow);
 
+            TRACE(5);
             mbar_wait(&tfull[acc], acc_phase);
+            TRACE(6);
             tc_fence_after();
             const float* bs = bias_s + acc * 256;
             const float* cs = csum_s + acc * 256;
@@ -435,6 +468,7 @@ __global__ void __launch_bounds__(n_threads(GEGLU), 1) gemm_tc_kernel(const __gr
                     // (t2v_model.py:819-821 under autocast: proj output, gelu output, product).  Bias / LayerNorm-fold
                     // vectors come from the staged smem tile, no residual, 32 B aligned fp16 rows (gemm_plan checks).
                     tmem_ld_wait();
+                    TRACE(7);
                     uint32_t ow[CW / 2];
 #pragma unroll
                     for (int j = 0; j < CW; j += 2) {
@@ -495,6 +529,7 @@ __global__ void __launch_bounds__(n_threads(GEGLU), 1) gemm_tc_kernel(const __gr
                     }
                 }
                 if constexpr (!kPipe) tmem_ld_wait();
+                TRACE(7);
                 float v[CW];
                 if (ln) {
 #pragma unroll
@@ -528,6 +563,7 @@ __global__ void __launch_bounds__(n_threads(GEGLU), 1) gemm_tc_kernel(const __gr
                     } else {
                         if (lane == 0) bulk_wait_read0();          // the previous chunk's store has finished READING the buffer
                     }
+                    TRACE(8);
                     __syncwarp();
                     const uint32_t rowb = my_stage + static_cast<uint32_t>(lane) * 64u;
                     const int sw = (lane >> 1) & 3;                // SWIZZLE_64B: 16-byte chunk ^= address bits [7,9)
@@ -542,6 +578,7 @@ __global__ void __launch_bounds__(n_threads(GEGLU), 1) gemm_tc_kernel(const __gr
                         sts_128(rowb + static_cast<uint32_t>((k ^ sw) << 4), w4[0], w4[1], w4[2], w4[3]);
                     }
                     fence_proxy_async();
+                    TRACE(9);
                     __syncwarp();
                     if (lane == 0 && !(g.flags & GEMM_DBG_NO_STORE) && tmi < g.tiles_m) {
                         const int c1 = torg[0] + g.st_off[q][0], c2 = torg[1] + g.st_off[q][1];
@@ -632,6 +669,7 @@ __global__ void __launch_bounds__(n_threads(GEGLU), 1) gemm_tc_kernel(const __gr
             }
             tc_fence_before();
             __syncwarp();
+            TRACE(10);
             if (lane == 0) {
                 if (CG == 2 && !leader) mbar_arrive_cluster(&tempty[acc], 0);   // the MMA issuer lives in the leader CTA
                 else mbar_arrive(&tempty[acc]);
@@ -999,3 +1037,11 @@ int gemm_launch(const GemmPlan& plan, cudaStream_t stream) {
 }
 
 }  // namespace t2v
+
+#if T2V_GEMM_TRACE
+// trace builds only (scripts/gemm_trace.py): device buffer of 2 * 4 * 4096 u64, or null to stop recording
+extern "C" int t2v_debug_gemm_trace(void* buf) {
+    unsigned long long* p = reinterpret_cast<unsigned long long*>(buf);
+    return cudaMemcpyToSymbol(t2v::g_trace_buf, &p, sizeof(p)) == cudaSuccess ? 0 : -1;
+}
+#endif

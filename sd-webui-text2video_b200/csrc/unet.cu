@@ -480,7 +480,7 @@ Tok transformer_block(Ctx& c, Tok x, const std::string& p, int heads, long long 
             ap_.q_ss = qkv.ld;
             ap_.k_bs = ap_.v_bs = static_cast<long long>(c.L) * kv.ld;
             ap_.k_ss = ap_.v_ss = kv.ld;
-            ap_.kv_batch_div = c.F;
+            ap_.kv_batch_div = c.Fl;          // frames per sample IN THIS MATRIX (frame-sharded clip: this rank's frames)
             ap_.o_bs = P * o.ld;
             ap_.o_ss = o.ld;
         }
@@ -881,7 +881,8 @@ int build(t2v_unet* u, Plan* plan, Arena* arena, bool dry, cudaStream_t stream, 
                     break;
             }
             if (sharded && b.kind == Blk::RES) x_ps = true;     // res_block ends in the temporal conv block (pixel-sharded)
-            tap(c, b.prefix, y, hc, wc);
+            if (sharded && x_ps) tap(c, b.prefix, y, 1, own_pixels(c, hc, wc));      // pixel-sharded: rows (b, f, own pixel)
+            else tap(c, b.prefix, y, hc, wc);
             release(x);
             x_is_io = false;
             x = y;
@@ -996,8 +997,8 @@ Plan* get_plan(t2v_unet* u, int B, int F, int h, int w, int L, cudaStream_t stre
     Arena arena;
     IO io;
     if (u->shard_on) {
-        if (u->cfg.arch != 0 || u->taps_enabled) {
-            set_error("frame sharding is built for the ModelScope UNetSD (arch 0) without parity taps");
+        if (u->cfg.arch != 0) {
+            set_error("frame sharding is built for the ModelScope UNetSD (arch 0)");
             return nullptr;
         }
         int deepest = h * w;
@@ -1317,6 +1318,20 @@ int t2v_unet_lora_merged(t2v_unet* u) { return u->params.merged_count(); }
 int t2v_unet_enable_taps(t2v_unet* u, int on) {
     u->taps_enabled = on != 0;
     return 0;
+}
+
+int t2v_unet_tap_info(t2v_unet* u, const char* name, long long* rows, int* C, int* h, int* w) {
+    for (auto& kv : u->plans) {
+        auto it = kv.second->taps.find(name);
+        if (it == kv.second->taps.end()) continue;
+        if (rows) *rows = it->second.first.rows;
+        if (C) *C = it->second.first.C;
+        if (h) *h = it->second.second.first;
+        if (w) *w = it->second.second.second;
+        return 0;
+    }
+    set_error("tap '%s' not found (enable taps before the forward)", name);
+    return -1;
 }
 
 long long t2v_unet_read_tap(t2v_unet* u, const char* name, void* dst, long long cap_elems, void* stream_) {

@@ -29,6 +29,7 @@ SIGNATURES = {
     't2v_unet_profile': (c_int, [P, c_int, c_int, c_int, c_int, c_int, P, C.POINTER(c_double)]),
     't2v_unet_read_tap': (c_ll, [P, c_char_p, P, c_ll, P]),
     't2v_unet_enable_taps': (c_int, [P, c_int]),
+    't2v_unet_tap_info': (c_int, [P, c_char_p, C.POINTER(c_ll), C.POINTER(c_int), C.POINTER(c_int), C.POINTER(c_int)]),
     't2v_unet_lora_merge': (c_int, [P, c_char_p, P, P, c_int, c_float, c_int, P]),
     't2v_unet_lora_clear': (c_int, [P, P]),
     't2v_unet_lora_merged': (c_int, [P]),

@@ -346,6 +346,12 @@ class UNetSD(_NativeModule):
             raise RuntimeError(f'read_tap({name}): {n} vs {out.numel()}: {_lib.load_library().t2v_last_error().decode()}')
         return out
 
+    def read_tap_auto(self, name):
+        """The tap as [(rows / (h w)), C, h, w] with the shape taken from the library (frame-sharded clips: see t2v_unet_tap_info)."""
+        rows, c, h, w = C.c_longlong(0), C.c_int(0), C.c_int(0), C.c_int(0)
+        _lib.check(_lib.lib().t2v_unet_tap_info(self._handle, name.encode(), C.byref(rows), C.byref(c), C.byref(h), C.byref(w)), 'tap_info')
+        return self.read_tap(name, (rows.value // (h.value * w.value), c.value, h.value, w.value))
+
 
 class UNetModel(UNetSD):
     """Drop-in for videocrafter/lvdm/models/modules/openaimodel3d.py::UNetModel as configured by

