@@ -60,7 +60,7 @@ def run_case(name, M, K, N, res, flags=0, taps=None, dims=None, geglu=False, for
             continue
         t0 = min(allt)
         span = max(allt) - t0
-        prod = [x[0] - t0 for x in ev[0]]
+        prod = [x[0] - t0 for x in ev[0] if x[1] == 1]
         mma_full = [x[0] - t0 for x in ev[1] if x[1] == 4]
         # per-k-iteration: TMA issue -> operands landed (same index: the ring is FIFO)
         lat = [m - p for p, m in zip(prod, mma_full)]

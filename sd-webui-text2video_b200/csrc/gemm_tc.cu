@@ -172,88 +172,130 @@ __global__ void __launch_bounds__(n_threads(GEGLU), 1) gemm_tc_kernel(const __gr
 
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer
-        if (lane == 0) {
-            TRACE_DECL(0);
+        // All 32 lanes run the loops with warp-uniform values and ONE ELECTED lane issues (elect.sync): inside an `if (lane == 0)`
+        // region the compiler cannot prove the operands of the uniform-datapath instructions (UTMALDG / UTCHMMA / UTCBAR) uniform and
+        // wraps every one of them in an ELECT + R2UR.BROADCAST + BRA.U.ANY "waterfall" loop -- measured with the in-kernel timeline:
+        // 240-320 clk per TMA issue, 496 clk for the four MMAs + commit of a stage, i.e. the ISSUING THREADS paced the pipe at
+        // ~700 clk per K step for every tile width (the tensor pipe needs 320-512).
+        {
+            TRACE_DECL(lane == 0 ? 0 : -1);
             int stage = 0;
             uint32_t phase = 0;
             if constexpr (BS) {
-                if (first_pair < total_items) {        // the resident weight slice: every (tap, K chunk) box of N-tile bs_tn, once
+                if (first_pair < total_items && elect_one()) {        // the resident weight slice: every (tap, K chunk) box of N-tile bs_tn, once
                     mbar_expect_tx(bfull, static_cast<uint32_t>(k_total * C::kBBytes));
-                    for (int it = 0; it < k_total; ++it) {
-                        const int tap = it / g.k_chunks;
-                        const int kc = it - tap * g.k_chunks;
+                    const int kch0 = g.k_chunks;
+                    for (int it = 0, tap = 0, kc = 0; it < k_total; ++it) {
                         tma_load_3d(sB_res + it * C::kBBytes, &g.map_b, bfull, kc * GEMM_BLOCK_K, bs_tn * BN, tap);
+                        if (++kc == kch0) {
+                            kc = 0;
+                            ++tap;
+                        }
                     }
                 }
+                __syncwarp();
             }
+            // The loop below is ONE thread's dependent instruction chain per k-iteration; the in-kernel timeline
+            // (profiles/r02_gemm_timeline.md) showed it at 700-900 clk per iteration -- integer divisions, indexed constant loads and
+            // the tile-origin div/mod chain -- i.e. SLOWER than the 320-512 clk the tensor pipe needs per stage, so the producer, not
+            // the MMA or L2, paced every K <= 640 layer.  Hence: kernel parameters hoisted into registers, (tap, K chunk) advanced
+            // by counters instead of divided out, tap offsets re-read only when the tap changes, plain row matrices (nd == 1)
+            // skip the origin div/mod chain.
+            const int kch = g.k_chunks, nd = g.nd, a_tx = g.a_tx_bytes, tiles_n_ = g.tiles_n, tiles_m_ = g.tiles_m;
+            const int bdim = g.b_batch_dim;
             for (int wi = first_pair; wi < total_items; wi += pair_stride) {
-                const int sp = BS ? 0 : wi % nsplit;
-                const int pt = wi / nsplit;
-                const int it0 = sp * k_per, it1 = min(k_total, it0 + k_per);
-                const int tn = BS ? bs_tn : pt % g.tiles_n;
-                const int tmi = BS ? wi : (pt / g.tiles_n) * CG + static_cast<int>(rank);
-                int tm = tmi;
-                int org[GEMM_MAX_RDIMS];
-#pragma unroll
-                for (int d = 0; d < GEMM_MAX_RDIMS; ++d) {
-                    const int td = g.tdim[d];
-                    org[d] = (tm % td) * g.box[d];
-                    tm /= td;
+                int sp = 0, pt = wi;
+                if (!BS && nsplit > 1) {
+                    sp = wi % nsplit;
+                    pt = wi / nsplit;
                 }
-                if (tmi >= g.tiles_m) org[0] = g.dim[0];       // odd tail: this CTA's half is all out of bounds (zeros)
-                const int bbatch = g.b_batch_dim >= 0 ? org[g.b_batch_dim] : 0;
-                {
-                    for (int it = it0; it < it1; ++it) {
-                        const int tap = it / g.k_chunks;
-                        const int kc = it - tap * g.k_chunks;
-                        const int c1 = org[0] + g.tap_off[tap][0];
-                        const int c2 = org[1] + g.tap_off[tap][1];
-                        const int c3 = org[2] + g.tap_off[tap][2];
-                        const int c4 = org[3] + g.tap_off[tap][3];
-                        mbar_wait(&empty[stage], phase ^ 1u);
-                        TRACE(1);
-                        uint8_t* sa = BS ? sA_ring + stage * kABytes : smem + stage * C::kStageBytes;
-                        uint8_t* sb = sa + kABytes;
-                        const int k0 = kc * GEMM_BLOCK_K;
-                        if constexpr (BS) {
-                            mbar_expect_tx(&full[stage], static_cast<uint32_t>(g.a_tx_bytes));
-                            switch (g.nd) {
-                                case 1: tma_load_2d(sa, &g.map_a, &full[stage], k0, c1); break;
-                                case 2: tma_load_3d(sa, &g.map_a, &full[stage], k0, c1, c2); break;
-                                case 3: tma_load_4d(sa, &g.map_a, &full[stage], k0, c1, c2, c3); break;
-                                default: tma_load_5d(sa, &g.map_a, &full[stage], k0, c1, c2, c3, c4); break;
-                            }
-                        } else if constexpr (CG == 2) {
-                            // both CTAs' bytes complete on the LEADER's barrier; only the leader arms it
-                            if (leader) mbar_expect_tx(&full[stage], static_cast<uint32_t>(2 * (g.a_tx_bytes + C::kBBytes)));
-                            const uint32_t lb = leader_bar_addr(&full[stage]);
-                            switch (g.nd) {
-                                case 1: tma_load_2d_2sm(sa, &g.map_a, lb, k0, c1); break;
-                                case 2: tma_load_3d_2sm(sa, &g.map_a, lb, k0, c1, c2); break;
-                                case 3: tma_load_4d_2sm(sa, &g.map_a, lb, k0, c1, c2, c3); break;
-                                default: tma_load_5d_2sm(sa, &g.map_a, lb, k0, c1, c2, c3, c4); break;
-                            }
-                            tma_load_3d_2sm(sb, &g.map_b, lb, k0, tn * BN + static_cast<int>(rank) * (BN / 2), tap + bbatch);
-                        } else {
-                            mbar_expect_tx(&full[stage], static_cast<uint32_t>(g.a_tx_bytes + C::kBBytes));
-                            switch (g.nd) {
-                                case 1: tma_load_2d(sa, &g.map_a, &full[stage], k0, c1); break;
-                                case 2: tma_load_3d(sa, &g.map_a, &full[stage], k0, c1, c2); break;
-                                case 3: tma_load_4d(sa, &g.map_a, &full[stage], k0, c1, c2, c3); break;
-                                default: tma_load_5d(sa, &g.map_a, &full[stage], k0, c1, c2, c3, c4); break;
-                            }
-                            tma_load_3d(sb, &g.map_b, &full[stage], k0, tn * BN, tap + bbatch);
+                const int it0 = sp * k_per, it1 = min(k_total, it0 + k_per);
+                int tn = bs_tn, tmi = wi;
+                if constexpr (!BS) {
+                    const int pm = pt / tiles_n_;
+                    tn = pt - pm * tiles_n_;
+                    tmi = pm * CG + static_cast<int>(rank);
+                }
+                int org[GEMM_MAX_RDIMS] = {0, 0, 0, 0};
+                if (nd == 1) {
+                    org[0] = tmi * g.box[0];
+                } else {
+                    int tm = tmi;
+#pragma unroll
+                    for (int d = 0; d < GEMM_MAX_RDIMS; ++d) {
+                        if (d < nd) {
+                            const int td = g.tdim[d];
+                            const int qd = tm / td;
+                            org[d] = (tm - qd * td) * g.box[d];
+                            tm = qd;
                         }
-                        if (++stage == nst) {
-                            stage = 0;
-                            phase ^= 1u;
+                    }
+                }
+                if (tmi >= tiles_m_) org[0] = g.dim[0];       // odd tail: this CTA's half is all out of bounds (zeros)
+                const int bbatch = bdim < 0 ? 0 : (bdim == 0 ? org[0] : (bdim == 1 ? org[1] : (bdim == 2 ? org[2] : org[3])));     // no indexed local array
+                int tap = 0, kc = it0;
+                if (it0 >= kch) {
+                    tap = it0 / kch;
+                    kc = it0 - tap * kch;
+                }
+                int c1 = org[0] + g.tap_off[tap][0], c2 = org[1] + g.tap_off[tap][1];
+                int c3 = org[2] + g.tap_off[tap][2], c4 = org[3] + g.tap_off[tap][3];
+                for (int it = it0; it < it1; ++it) {
+                    mbar_wait(&empty[stage], phase ^ 1u);
+                    TRACE(1);
+                    uint8_t* sa = BS ? sA_ring + stage * kABytes : smem + stage * C::kStageBytes;
+                    uint8_t* sb = sa + kABytes;
+                    const int k0 = kc * GEMM_BLOCK_K;
+                    if (elect_one()) {
+                    if constexpr (BS) {
+                        mbar_expect_tx(&full[stage], static_cast<uint32_t>(a_tx));
+                        TRACE(11);
+                        if (nd == 1) tma_load_2d(sa, &g.map_a, &full[stage], k0, c1);
+                        else if (nd == 2) tma_load_3d(sa, &g.map_a, &full[stage], k0, c1, c2);
+                        else if (nd == 3) tma_load_4d(sa, &g.map_a, &full[stage], k0, c1, c2, c3);
+                        else tma_load_5d(sa, &g.map_a, &full[stage], k0, c1, c2, c3, c4);
+                        TRACE(12);
+                    } else if constexpr (CG == 2) {
+                        // both CTAs' bytes complete on the LEADER's barrier; only the leader arms it
+                        if (leader) mbar_expect_tx(&full[stage], static_cast<uint32_t>(2 * (a_tx + C::kBBytes)));
+                        const uint32_t lb = leader_bar_addr(&full[stage]);
+                        if (nd == 1) tma_load_2d_2sm(sa, &g.map_a, lb, k0, c1);
+                        else if (nd == 2) tma_load_3d_2sm(sa, &g.map_a, lb, k0, c1, c2);
+                        else if (nd == 3) tma_load_4d_2sm(sa, &g.map_a, lb, k0, c1, c2, c3);
+                        else tma_load_5d_2sm(sa, &g.map_a, lb, k0, c1, c2, c3, c4);
+                        tma_load_3d_2sm(sb, &g.map_b, lb, k0, tn * BN + static_cast<int>(rank) * (BN / 2), tap + bbatch);
+                    } else {
+                        mbar_expect_tx(&full[stage], static_cast<uint32_t>(a_tx + C::kBBytes));
+                        TRACE(11);
+                        if (nd == 1) tma_load_2d(sa, &g.map_a, &full[stage], k0, c1);
+                        else if (nd == 2) tma_load_3d(sa, &g.map_a, &full[stage], k0, c1, c2);
+                        else if (nd == 3) tma_load_4d(sa, &g.map_a, &full[stage], k0, c1, c2, c3);
+                        else tma_load_5d(sa, &g.map_a, &full[stage], k0, c1, c2, c3, c4);
+                        TRACE(12);
+                        tma_load_3d(sb, &g.map_b, &full[stage], k0, tn * BN, tap + bbatch);
+                        TRACE(13);
+                    }
+                    }   // elected lane
+                    __syncwarp();
+                    if (++kc == kch) {              // next tap: new coordinate offsets (at most 9 times per tile)
+                        kc = 0;
+                        ++tap;
+                        if (it + 1 < it1) {
+                            c1 = org[0] + g.tap_off[tap][0];
+                            c2 = org[1] + g.tap_off[tap][1];
+                            c3 = org[2] + g.tap_off[tap][2];
+                            c4 = org[3] + g.tap_off[tap][3];
                         }
+                    }
+                    if (++stage == nst) {
+                        stage = 0;
+                        phase ^= 1u;
                     }
                 }
             }
             // nothing left to fetch: only this CTA's last MMAs / epilogue remain -> let the next kernel's CTAs be scheduled
             // (they run their prologue and block in griddepcontrol.wait until this grid has completed)
-            griddep_launch();
+            if (lane == 0) griddep_launch();
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer (pair leader only)
@@ -282,7 +324,7 @@ __global__ void __launch_bounds__(n_threads(GEGLU), 1) gemm_tc_kernel(const __gr
                 mbar_wait(&full[stage], phase);
                 TRACE(4);
                 tc_fence_after();
-                if (lane == 0) {
+                if (elect_one()) {
                     const bool skip_mma = (g.flags & GEMM_DBG_NO_MMA) != 0;
                     const uint32_t sa = smem_u32(BS ? sA_ring + stage * kABytes : smem + stage * C::kStageBytes);
                     const uint64_t da = umma_desc_k_sw128(sa);
@@ -305,6 +347,7 @@ __global__ void __launch_bounds__(n_threads(GEGLU), 1) gemm_tc_kernel(const __gr
                         umma_commit(&empty[stage]);                       // smem stage reusable once these MMAs retire
                         if (it == k_iters - 1) umma_commit(&tfull[acc]);  // accumulator complete
                     }
+                    TRACE(14);
                 }
                 __syncwarp();
                 if (++stage == nst) {
@@ -359,8 +402,13 @@ __global__ void __launch_bounds__(n_threads(GEGLU), 1) gemm_tc_kernel(const __gr
             long long grow = 0;
             long long mul = 1;
             bool valid = tmi < g.tiles_m;
-            int torg[GEMM_MAX_RDIMS];                  // tile origin in the row grid (TMA-store coordinates)
-            {
+            int torg[GEMM_MAX_RDIMS] = {0, 0, 0, 0};   // tile origin in the row grid (TMA-store coordinates)
+            if (g.nd == 1) {                           // plain row matrix: no div/mod chain (16 integer divisions per tile otherwise)
+                const int o = tmi * g.box[0];
+                torg[0] = o;
+                valid = valid && (r < g.box[0]) && (o + r < g.dim[0]);
+                grow = o + r;
+            } else {
                 int rr = r;
 #pragma unroll
                 for (int d = 0; d < GEMM_MAX_RDIMS; ++d) {
@@ -557,11 +605,13 @@ __global__ void __launch_bounds__(n_threads(GEGLU), 1) gemm_tc_kernel(const __gr
                         }
                     }
                     const uint32_t my_stage = my_stage0 + (kStage2 ? stage_bank * 16384u : 0u);
+                    // bulk async-groups belong to the committing THREAD: issue, commit and wait all sit behind elect.sync (same
+                    // membermask -> same lane every time), which also keeps the UTMASTG free of a waterfall loop
                     if constexpr (kStage2) {
-                        if (lane == 0) bulk_wait_read1();          // the store before the previous one has finished READING this bank
+                        if (elect_one()) bulk_wait_read1();        // the store before the previous one has finished READING this bank
                         stage_bank ^= 1u;
                     } else {
-                        if (lane == 0) bulk_wait_read0();          // the previous chunk's store has finished READING the buffer
+                        if (elect_one()) bulk_wait_read0();        // the previous chunk's store has finished READING the buffer
                     }
                     TRACE(8);
                     __syncwarp();
@@ -580,7 +630,7 @@ __global__ void __launch_bounds__(n_threads(GEGLU), 1) gemm_tc_kernel(const __gr
                     fence_proxy_async();
                     TRACE(9);
                     __syncwarp();
-                    if (lane == 0 && !(g.flags & GEMM_DBG_NO_STORE) && tmi < g.tiles_m) {
+                    if (!(g.flags & GEMM_DBG_NO_STORE) && tmi < g.tiles_m && elect_one()) {
                         const int c1 = torg[0] + g.st_off[q][0], c2 = torg[1] + g.st_off[q][1];
                         const int c3 = torg[2] + g.st_off[q][2], c4 = torg[3] + g.st_off[q][3];
                         switch (g.nd) {
@@ -679,7 +729,9 @@ __global__ void __launch_bounds__(n_threads(GEGLU), 1) gemm_tc_kernel(const __gr
         }
     }
 
-    if (warp >= 2 && lane == 0) bulk_wait0();     // TMA stores issued by this thread have left the staging buffer
+    if (warp >= 2) {
+        if (elect_one()) bulk_wait0();            // TMA stores issued by this (elected) thread have left the staging buffer
+    }
     tc_fence_before();
     if constexpr (CG == 2) cluster_sync_all();    // no CTA may exit (or free TMEM) while its peer can still signal it
     else __syncthreads();
