@@ -783,6 +783,7 @@ Variant variant_bs() {
 const Variant* variants(int* n) {
     static const Variant v[] = {
         variant<16, false, 1>(),  variant<64, false, 1>(),  variant<128, false, 1>(), variant<160, false, 1>(),
+        variant<192, false, 1>(), variant<224, false, 1>(),
         variant<256, false, 1>(), variant<64, true, 1>(),   variant<128, true, 1>(),  variant<256, true, 1>(),
         variant<64, false, 2>(),  variant<128, false, 2>(), variant<160, false, 2>(), variant<256, false, 2>(),
         variant<64, true, 2>(),   variant<128, true, 2>(),  variant<256, true, 2>(),
@@ -929,11 +930,46 @@ int gemm_plan(const GemmProblem& p, GemmPlan* plan, int num_sms) {
     g.splits = p.splits > 1 ? p.splits : 1;
     g.split_stride = p.split_stride;
 
-    // ---- N tiling: widest tile that keeps the machine full
+    // ---- N tiling: the tile width with the shortest modelled kernel time.  The in-kernel timeline (profiles/r02_gemm_timeline.md)
+    // shows a K step costing the issuing threads ~600 clk whatever the tile width (the tensor pipe itself needs 2 clk per
+    // column: 512 clk at BN = 256), and a tile's epilogue ~1000 clk per 32-column chunk per warp (2 warps share a quadrant's
+    // chunks; twice that with a residual to fetch).  A persistent CTA walks ceil(tiles / CTAs) tiles whose MMA and epilogue
+    // overlap (double-buffered accumulator), plus one exposed epilogue at the end.  So: as few K steps per CTA as possible --
+    // wide tiles, even slightly padded ones (N = 1920 -> 9 x 224 instead of 12 x 160), unless the epilogue is the longer leg.
     int bn = p.force_bn;
+    const int k_total_sel = p.ntaps * g.k_chunks;
+    if (bn == 0 && k_total_sel >= 10) {
+        // K-heavy tiles (>= 10 K steps): the MMA leg dominates -> time model, padded wide tiles allowed.  Measured (B200,
+        // profiles/r02_gemm_tile_widths.txt): N = 1920, K = 640: 12 x 160 -> 9 x 224 columns 34.7 -> 30.2 us.
+        const int cands[7] = {256, 224, 192, 160, 128, 64, 16};
+        double best = 1e30;
+        for (int i = 0; i < 7; ++i) {
+            const int c = cands[i];
+            if ((p.flags & GEMM_GEGLU) && c != 256 && c != 128 && c != 64) continue;
+            if (c == 16 && p.N > 16) continue;
+            if (c > 16 && p.N <= 16) continue;
+            if ((c == 224 || c == 192) && ((p.flags & GEMM_GEGLU) || p.b_batch_dim >= 0 || p.splits > 1)) continue;   // plain variants only
+            const int tn = (p.N + c - 1) / c;
+            if ((p.flags & GEMM_GEGLU) && (p.N % c) != 0) continue;
+            const long long tiles = static_cast<long long>(tn) * g.tiles_m * g.splits;
+            const long long ctas = std::min<long long>(tiles, num_sms);
+            const long long per_cta = (tiles + ctas - 1) / ctas;
+            const int k_iters = g.splits > 1 ? (k_total_sel + g.splits - 1) / g.splits : k_total_sel;
+            const double t_iter = std::max(650.0, 2.7 * c);
+            const int chunks_per_warp = c >= 64 ? (c / 32 + 1) / 2 : 1;
+            const double t_epi = 900.0 + chunks_per_warp * (p.residual != nullptr ? 2100.0 : 1050.0);
+            const double t_tile = std::max(k_iters * t_iter, t_epi) + 1500.0;
+            const double fit = static_cast<double>(p.N) / (static_cast<double>(tn) * c);
+            const double t = (per_cta * t_tile + t_epi) * (1.0 + 0.02 * (1.0 - fit));
+            if (t < best) {
+                best = t;
+                bn = c;
+            }
+        }
+    }
     if (bn == 0) {
+        // few K steps per tile (K = 320 layers): prologue / epilogue legs dominate and the measured optimum is the exact-fit width
         const int cands[5] = {256, 160, 128, 64, 16};
-        // relative tile efficiency measured on B200 (scripts/gemm_isolate.py): wide tiles move fewer operand bytes per flop
         const double eff[5] = {1.0, 0.86, 0.80, 0.55, 0.25};
         double best = -1;
         for (int i = 0; i < 5; ++i) {
@@ -970,7 +1006,7 @@ int gemm_plan(const GemmProblem& p, GemmPlan* plan, int num_sms) {
     // on the K = 320 layers), so pairs are opt-in (T2V_2CTA=1 or force_cg) until the pair path gets TMA multicast.
     static const bool use_pairs = getenv("T2V_2CTA") != nullptr;
     plan->cg = p.force_cg ? p.force_cg : ((g.tiles_m >= 2 && bn >= 64 && use_pairs) ? 2 : 1);
-    if (bn < 64 || p.b_batch_dim >= 0 || plan->bs) plan->cg = 1;     // a pair shares ONE B tile: never across B batches
+    if (bn < 64 || p.b_batch_dim >= 0 || plan->bs || bn == 192 || bn == 224) plan->cg = 1;     // a pair shares ONE B tile: never across B batches
     g.tiles_n = (p.N + bn - 1) / bn;
     if ((p.flags & GEMM_GEGLU) && (p.N % bn) != 0) {
         fprintf(stderr, "[t2v_b200] gemm_plan: GEGLU needs N %% BN == 0 (N %d BN %d)\n", p.N, bn);
