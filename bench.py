@@ -46,6 +46,8 @@ def parse():
                     help='N>1: sample_dp = one clip per GPU (weak scaling, the default the driver runs); frame_shard = ONE clip '
                          'split over the N GPUs by frames (strong scaling, BASELINE config 4: --frames 125); frame_shard_cfg = the same '
                          'with the guidance pair split as well: N/2 frame shards x (cond | uncond), one eps exchange per step')
+    ap.add_argument('--no-shard-leg', action='store_true', help='skip the secondary strong-scaling measurement (ONE 125-frame clip '
+                                                                'frame-sharded over all N GPUs; at N = 1 the same clip on one GPU)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-gpu-baseline', action='store_true', help='skip the torch-eager GPU comparator leg of the N=1 run')
     ap.add_argument('--cpu-frames', type=int, default=0, help='frames of the CPU sample (0 = the metric\'s F)')
@@ -362,18 +364,71 @@ def run_b200(args):
     ms_e2e = timed(clip_e2e, args.steps, 123, False)
     fps_e2e = n_units * args.steps * F / (ms_e2e / 1000.0)
 
+    prof = None
+    unet = pipe.sd_model
+    # work / launch counts of the measured mode: taken before the model is switched to frame-shard mode by the secondary leg below
+    # sharded: flops() is this rank's share (frame_shard_cfg: B = 1 per rank, half the ranks per branch)
+    unet_flops = (unet.flops(1, F, h, w, 77) * world if args.mode == 'frame_shard_cfg' and fs is not None else
+                  unet.flops(2, F, h, w, 77) * (world if fs is not None else 1))
+    vae_flops = pipe.autoencoder.flops(F, h, w)
+    launches_clip = S * (unet.num_launches() + 3) + 120
+    n_exchanges = unet.num_exchanges(F) if fs is not None else 0
+    if rank == 0:       # per-launch CUDA-event profile of one forward
+        prof = (unet.profile(2, F, h, w, 77) if fs is None else
+                {'gemm': {'ms': 0.0, 'flop': 0.0, 'launches': 0}, 'total_ms': 0.0})
+
+    # ---- secondary measurement, default mode only: BASELINE config 4, ONE 125-frame 256x256 clip, strong scaling.  N = 1: the clip
+    # on one GPU; N > 1: frame-sharded over all N GPUs (activations exchanged inside the UNet kernels over NVLink peer memory, one
+    # NCCL all-gather of the final latent, frame-sharded VAE).  1 warm-up clip (plan build + graph capture) + 1 timed clip.
+    shard_leg = None
+    if args.mode == 'sample_dp' and not args.no_shard_leg and args.frames == 24:
+        F4 = 125
+        try:
+            fs4 = pipe.enable_frame_shard() if world > 1 else None
+
+            def clip125(seed):
+                x_T = torch.randn((1, 4, F4, h, w), device=dev, generator=torch.Generator(device=dev).manual_seed(seed))
+                smp = entry.init_sampler(pipe.sd_model, betas=pipe.diffusion.betas, device=dev)
+                if fs4 is None:
+                    x0 = smp.sample(S=S, conditioning=c_dev, unconditional_conditioning=uc_dev, unconditional_guidance_scale=args.cfg_scale,
+                                    x_T=x_T, shape=tuple(x_T.shape), eta=0.0, batch_size=1)
+                    return pipe.autoencoder.decode_video(x0, 1.0 / SCALE_FACTOR, as_uint8=True)
+                fs4.begin(F4, seed)
+                try:
+                    x_l = fs4.local(x_T)
+                    x0 = smp.sample(S=S, conditioning=c_dev, unconditional_conditioning=uc_dev,
+                                    unconditional_guidance_scale=args.cfg_scale, x_T=x_l, shape=tuple(x_l.shape), eta=0.0, batch_size=1)
+                finally:
+                    fs4.end()
+                return fs4.decode(fs4.gather_latent(x0), 1.0 / SCALE_FACTOR)
+            clip125(2000)
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            clip125(2001)
+            e1.record()
+            torch.cuda.synchronize()
+            ms4 = torch.tensor([e0.elapsed_time(e1)], device=dev)
+            if world > 1:
+                dist.all_reduce(ms4, op=dist.ReduceOp.MAX)
+            ms4 = float(ms4.item())
+            shard_leg = {'workload': f'ModelScope UNetSD {F4}f x {H}x{Wd}, {S}-step {args.sampler}, ONE clip' +
+                                     (f' frame-sharded over {world} GPUs' if world > 1 else ' on one GPU'),
+                         'scaling': 'strong', 'n_gpus': world, 'value': F4 / (ms4 / 1000.0), 'unit': 'frames/s', 'ms_per_clip': ms4,
+                         'clips_timed': 1, 'exchanges_per_forward': pipe.sd_model.num_exchanges(F4) if world > 1 else 0,
+                         'collectives': 'none inside the sampling loop; 1 NCCL all-gather of the latent + 1 of the decoded frames per clip'
+                                        if world > 1 else 'none'}
+        except Exception as ex:                     # never lose the headline number over the secondary leg
+            shard_leg = {'error': str(ex)[:300]}
+
     if rank == 0:
         pk = peaks()
-        unet = pipe.sd_model
-        prof = unet.profile(2, F, h, w, 77) if fs is None else {'gemm': {'ms': 0.0, 'flop': 0.0, 'launches': 0}, 'total_ms': 0.0}
         gemm = prof['gemm']
         achieved = gemm['flop'] / (gemm['ms'] * 1e-3) / 1e12 if gemm['ms'] > 0 else 0.0
-        # sharded: flops() is this rank's share (frame_shard_cfg: B = 1 per rank, half the ranks per branch)
-        unet_flops = (unet.flops(1, F, h, w, 77) * world if args.mode == 'frame_shard_cfg' and fs is not None else
-                      unet.flops(2, F, h, w, 77) * (world if fs is not None else 1))
-        vae_flops = pipe.autoencoder.flops(F, h, w)
         clip_flops = S * unet_flops + vae_flops
-        launches_clip = S * (unet.num_launches() + 3) + 120
         # per GPU: a clip-rendering unit (one GPU, or a CFG pair) finishes one clip every ms / steps
         whole_clip_tflops = clip_flops / (ms / args.steps * 1e-3) / 1e12 / (world / n_units)
         line = {
@@ -385,7 +440,7 @@ def run_b200(args):
                                    f'cond+uncond forward, + AutoencoderKL decode of {F} frames',
                        'parallelism': ((f'CFG split x frame-shard ({world // 2} shards x 2 branches): ' if args.mode == 'frame_shard_cfg' else '') +
                                        f'frame-shard x{world}: ONE clip, {F} frames split over the GPUs; activations exchanged inside the UNet '
-                                       f'kernels over NVLink peer memory ({unet.num_exchanges(F)} layout exchanges per forward, no NCCL call per '
+                                       f'kernels over NVLink peer memory ({n_exchanges} layout exchanges per forward, no NCCL call per '
                                        'step), one NCCL all-gather of the final latent before a frame-sharded VAE' if fs is not None else
                                        f'sample-DP x{world} (one clip per GPU, one NCCL all-gather of the decoded clips)' if n_units == world else
                                        f'CFG-pair split: {n_units} pair(s) of GPUs, cond / uncond branch per GPU, one eps all-gather per step'),
@@ -405,6 +460,8 @@ def run_b200(args):
                          'gemm_share_of_forward': gemm['ms'] / prof['total_ms'] if prof['total_ms'] else None,
                          'forward_breakdown_ms': {k: round(v['ms'], 3) for k, v in prof.items() if isinstance(v, dict)}},
         }
+        if shard_leg is not None:
+            line['frame_shard_125f'] = shard_leg
         if world == 1 and not args.no_gpu_baseline:
             # the ">= 15x" denominator of BASELINE.json's north_star: the reference's fp16 PyTorch path on this same GPU
             try:

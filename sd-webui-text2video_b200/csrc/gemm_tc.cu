@@ -938,7 +938,8 @@ int gemm_plan(const GemmProblem& p, GemmPlan* plan, int num_sms) {
     // wide tiles, even slightly padded ones (N = 1920 -> 9 x 224 instead of 12 x 160), unless the epilogue is the longer leg.
     int bn = p.force_bn;
     const int k_total_sel = p.ntaps * g.k_chunks;
-    if (bn == 0 && k_total_sel >= 10) {
+    static const int model_min_k = getenv("T2V_BN_MODEL_MINK") ? atoi(getenv("T2V_BN_MODEL_MINK")) : 10;      // A/B switch
+    if (bn == 0 && k_total_sel >= model_min_k) {
         // K-heavy tiles (>= 10 K steps): the MMA leg dominates -> time model, padded wide tiles allowed.  Measured (B200,
         // profiles/r02_gemm_tile_widths.txt): N = 1920, K = 640: 12 x 160 -> 9 x 224 columns 34.7 -> 30.2 us.
         const int cands[7] = {256, 224, 192, 160, 128, 64, 16};
