@@ -38,6 +38,11 @@ namespace {
 #ifndef T2V_EPI_PIPE
 #define T2V_EPI_PIPE 0
 #endif
+// T2V_MMA_UNROLL2: two ring stages per MMA-loop trip (one wait / fence per 8 MMAs).  Measured SLOWER (forward 22.77 vs 21.91 ms,
+// profiles/r02_gemm_single_thread_roles_ab.txt): waiting for the second stage delays the first MMAs more than the saved loop trip.
+#ifndef T2V_MMA_UNROLL2
+#define T2V_MMA_UNROLL2 0
+#endif
 #ifndef T2V_EPI_STAGE2
 #define T2V_EPI_STAGE2 0
 #endif
@@ -172,17 +177,17 @@ __global__ void __launch_bounds__(n_threads(GEGLU), 1) gemm_tc_kernel(const __gr
 
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer
-        // All 32 lanes run the loops with warp-uniform values and ONE ELECTED lane issues (elect.sync): inside an `if (lane == 0)`
-        // region the compiler cannot prove the operands of the uniform-datapath instructions (UTMALDG / UTCHMMA / UTCBAR) uniform and
-        // wraps every one of them in an ELECT + R2UR.BROADCAST + BRA.U.ANY "waterfall" loop -- measured with the in-kernel timeline:
-        // 240-320 clk per TMA issue, 496 clk for the four MMAs + commit of a stage, i.e. the ISSUING THREADS paced the pipe at
-        // ~700 clk per K step for every tile width (the tensor pipe needs 320-512).
-        {
-            TRACE_DECL(lane == 0 ? 0 : -1);
+        // ONE ELECTED lane (elect.sync) runs the whole loop.  Inside an `if (lane == 0)` region the compiler cannot prove the
+        // operands of the uniform-datapath instructions (UTMALDG / UTCHMMA / UTCBAR) uniform and wraps every one of them in an
+        // ELECT + R2UR.BROADCAST + BRA.U.ANY "waterfall" loop -- measured with the in-kernel timeline: 240-320 clk per TMA issue,
+        // 496 clk for the four MMAs + commit of a stage, i.e. the ISSUING THREADS paced the pipe at ~700 clk per K step for
+        // every tile width (the tensor pipe needs 320-512).  An elect.sync region is compiled as single-threaded code.
+        if (elect_one()) {
+            TRACE_DECL(0);
             int stage = 0;
             uint32_t phase = 0;
             if constexpr (BS) {
-                if (first_pair < total_items && elect_one()) {        // the resident weight slice: every (tap, K chunk) box of N-tile bs_tn, once
+                if (first_pair < total_items) {        // the resident weight slice: every (tap, K chunk) box of N-tile bs_tn, once
                     mbar_expect_tx(bfull, static_cast<uint32_t>(k_total * C::kBBytes));
                     const int kch0 = g.k_chunks;
                     for (int it = 0, tap = 0, kc = 0; it < k_total; ++it) {
@@ -193,7 +198,6 @@ __global__ void __launch_bounds__(n_threads(GEGLU), 1) gemm_tc_kernel(const __gr
                         }
                     }
                 }
-                __syncwarp();
             }
             // The loop below is ONE thread's dependent instruction chain per k-iteration; the in-kernel timeline
             // (profiles/r02_gemm_timeline.md) showed it at 700-900 clk per iteration -- integer divisions, indexed constant loads and
@@ -246,7 +250,6 @@ __global__ void __launch_bounds__(n_threads(GEGLU), 1) gemm_tc_kernel(const __gr
                     uint8_t* sa = BS ? sA_ring + stage * kABytes : smem + stage * C::kStageBytes;
                     uint8_t* sb = sa + kABytes;
                     const int k0 = kc * GEMM_BLOCK_K;
-                    if (elect_one()) {
                     if constexpr (BS) {
                         mbar_expect_tx(&full[stage], static_cast<uint32_t>(a_tx));
                         TRACE(11);
@@ -275,8 +278,6 @@ __global__ void __launch_bounds__(n_threads(GEGLU), 1) gemm_tc_kernel(const __gr
                         tma_load_3d(sb, &g.map_b, &full[stage], k0, tn * BN, tap + bbatch);
                         TRACE(13);
                     }
-                    }   // elected lane
-                    __syncwarp();
                     if (++kc == kch) {              // next tap: new coordinate offsets (at most 9 times per tile)
                         kc = 0;
                         ++tap;
@@ -295,13 +296,14 @@ __global__ void __launch_bounds__(n_threads(GEGLU), 1) gemm_tc_kernel(const __gr
             }
             // nothing left to fetch: only this CTA's last MMAs / epilogue remain -> let the next kernel's CTAs be scheduled
             // (they run their prologue and block in griddepcontrol.wait until this grid has completed)
-            if (lane == 0) griddep_launch();
+            griddep_launch();
         }
+        __syncwarp();
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer (pair leader only)
         constexpr uint32_t idesc = umma_idesc_f16(GEMM_BLOCK_M * CG, BN);
-        if (leader) {
-        TRACE_DECL(lane == 0 ? 1 : -1);
+        if (leader && elect_one()) {
+        TRACE_DECL(1);
         int stage = 0;
         uint32_t phase = 0;
         int acc = 0;
@@ -320,45 +322,66 @@ __global__ void __launch_bounds__(n_threads(GEGLU), 1) gemm_tc_kernel(const __gr
             TRACE(3);
             tc_fence_after();
             const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * 256);
+            auto issue_stage = [&](int st, int it) {
+                const bool skip_mma = (g.flags & GEMM_DBG_NO_MMA) != 0;
+                const uint32_t sa = smem_u32(BS ? sA_ring + st * kABytes : smem + st * C::kStageBytes);
+                const uint64_t da = umma_desc_k_sw128(sa);
+                const uint64_t db = umma_desc_k_sw128(BS ? smem_u32(sB_res + it * C::kBBytes) : sa + kABytes);
+#pragma unroll
+                for (int k = 0; k < GEMM_BLOCK_K / 16; ++k) {
+                    if (skip_mma) break;
+                    // +32 B per K=16 step: start-address field is in 16 B units
+                    if constexpr (CG == 2)
+                        umma_f16_2sm(tmem_d, da + static_cast<uint64_t>(k * 2), db + static_cast<uint64_t>(k * 2), idesc,
+                                     (it | k) != 0 ? 1u : 0u);
+                    else
+                        umma_f16(tmem_d, da + static_cast<uint64_t>(k * 2), db + static_cast<uint64_t>(k * 2), idesc,
+                                 (it | k) != 0 ? 1u : 0u);
+                }
+                if constexpr (CG == 2) {
+                    umma_commit_2sm(&empty[st]);                          // frees the stage in BOTH CTAs
+                    if (it == k_iters - 1) umma_commit_2sm(&tfull[acc]);  // both epilogues may drain their half
+                } else {
+                    umma_commit(&empty[st]);                          // smem stage reusable once these MMAs retire
+                    if (it == k_iters - 1) umma_commit(&tfull[acc]);  // accumulator complete
+                }
+                TRACE(14);
+            };
+#if T2V_MMA_UNROLL2
+            // two ring stages per loop trip: one wait / fence / loop-around per 8 MMAs instead of per 4
+            for (int it = 0; it < k_iters; it += 2) {
+                const bool two = it + 1 < k_iters;
+                const bool wrap = stage + 1 == nst;
+                const int st2 = wrap ? 0 : stage + 1;
+                mbar_wait(&full[stage], phase);
+                if (two) mbar_wait(&full[st2], wrap ? phase ^ 1u : phase);
+                TRACE(4);
+                tc_fence_after();
+                issue_stage(stage, it);
+                if (two) issue_stage(st2, it + 1);
+                for (int a = 0; a < (two ? 2 : 1); ++a)
+                    if (++stage == nst) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+            }
+#else
             for (int it = 0; it < k_iters; ++it) {
                 mbar_wait(&full[stage], phase);
                 TRACE(4);
                 tc_fence_after();
-                if (elect_one()) {
-                    const bool skip_mma = (g.flags & GEMM_DBG_NO_MMA) != 0;
-                    const uint32_t sa = smem_u32(BS ? sA_ring + stage * kABytes : smem + stage * C::kStageBytes);
-                    const uint64_t da = umma_desc_k_sw128(sa);
-                    const uint64_t db = umma_desc_k_sw128(BS ? smem_u32(sB_res + it * C::kBBytes) : sa + kABytes);
-#pragma unroll
-                    for (int k = 0; k < GEMM_BLOCK_K / 16; ++k) {
-                        if (skip_mma) break;
-                        // +32 B per K=16 step: start-address field is in 16 B units
-                        if constexpr (CG == 2)
-                            umma_f16_2sm(tmem_d, da + static_cast<uint64_t>(k * 2), db + static_cast<uint64_t>(k * 2), idesc,
-                                         (it | k) != 0 ? 1u : 0u);
-                        else
-                            umma_f16(tmem_d, da + static_cast<uint64_t>(k * 2), db + static_cast<uint64_t>(k * 2), idesc,
-                                     (it | k) != 0 ? 1u : 0u);
-                    }
-                    if constexpr (CG == 2) {
-                        umma_commit_2sm(&empty[stage]);                       // frees the stage in BOTH CTAs
-                        if (it == k_iters - 1) umma_commit_2sm(&tfull[acc]);  // both epilogues may drain their half
-                    } else {
-                        umma_commit(&empty[stage]);                       // smem stage reusable once these MMAs retire
-                        if (it == k_iters - 1) umma_commit(&tfull[acc]);  // accumulator complete
-                    }
-                    TRACE(14);
-                }
-                __syncwarp();
+                issue_stage(stage, it);
                 if (++stage == nst) {
                     stage = 0;
                     phase ^= 1u;
                 }
             }
+#endif
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1u;
         }
-        }   // leader
+        }   // leader's elected thread
+        __syncwarp();
     } else {
         // ------------------------------------------------------------------ epilogue (warps 2..9)
         // 8 warps: TMEM lane quadrant q = warp & 3 (a warp may only touch lanes 32q..32q+31), column chunks are
