@@ -37,29 +37,49 @@ __global__ void __launch_bounds__(kXThreads) shard_exchange_kernel(const XchgPar
     }
     const __half* src = p.src;
     __half* dst = p.dst[s];
-    const long long stride = static_cast<long long>(nblk) * kXThreads;
+    // vector index -> (sample, frame, pixel, 16-byte chunk) without integer divisions in the copy loop: the three divisors are
+    // block constants, so thread 0 derives round-up magic numbers once (Granlund-Montgomery: q = (t + ((n - t) >> s1)) >> s2 with
+    // t = umulhi(m, n), exact for every 32-bit n); the 64-bit div/mod chain cost ~300 instructions per 16 bytes before.
+    __shared__ uint32_t fd[3][3];
+    if (threadIdx.x < 3) {
+        uint32_t d = threadIdx.x == 0 ? static_cast<uint32_t>(C8) : (threadIdx.x == 1 ? static_cast<uint32_t>(np) : static_cast<uint32_t>(nf));
+        if (d == 0u) d = 1u;          // empty block (nvec = 0): the constants are never used
+        uint32_t l = 0;
+        while ((1u << l) < d) ++l;
+        fd[threadIdx.x][0] = static_cast<uint32_t>(((1ull << 32) * ((1ull << l) - d)) / d) + 1u;
+        fd[threadIdx.x][1] = l < 1u ? l : 1u;
+        fd[threadIdx.x][2] = l - (l < 1u ? l : 1u);
+    }
+    __syncthreads();
+    auto fdiv = [&](uint32_t n, int i) {
+        const uint32_t t = __umulhi(fd[i][0], n);
+        return (t + ((n - t) >> fd[i][1])) >> fd[i][2];
+    };
+    const uint32_t nv32 = static_cast<uint32_t>(nvec);
+    const uint32_t stride = static_cast<uint32_t>(nblk) * kXThreads;
+    const long long rbase_s = p.to_ps ? static_cast<long long>(p.pb[s]) : 0, rbase_d = p.to_ps ? 0 : static_cast<long long>(p.pb[me]);
     constexpr int U = 4;
-    for (long long v0 = static_cast<long long>(j) * kXThreads + threadIdx.x; v0 < nvec; v0 += U * stride) {
+    for (uint32_t v0 = static_cast<uint32_t>(j) * kXThreads + threadIdx.x; v0 < nv32; v0 += U * stride) {
         uint4 val[U];
         long long doff[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const long long v = v0 + u * stride;
+            const uint32_t v = v0 + u * stride;
             doff[u] = -1;
-            if (v < nvec) {
-                const long long row = v / C8;
-                const int vc = static_cast<int>(v - row * C8);
-                const long long bf = row / np;
-                const int pl = static_cast<int>(row - bf * np);
-                const int b = static_cast<int>(bf / nf);
-                const int fl = static_cast<int>(bf - static_cast<long long>(b) * nf);
+            if (v < nv32) {
+                const uint32_t row = fdiv(v, 0);
+                const uint32_t vc = v - row * static_cast<uint32_t>(C8);
+                const uint32_t bf = fdiv(row, 1);
+                const uint32_t pl = row - bf * static_cast<uint32_t>(np);
+                const uint32_t b = fdiv(bf, 2);
+                const uint32_t fl = bf - b * static_cast<uint32_t>(nf);
                 long long srow, drow;
                 if (p.to_ps) {
-                    srow = (static_cast<long long>(b) * nf_me + fl) * p.P + p.pb[s] + pl;
+                    srow = (static_cast<long long>(b) * nf_me + fl) * p.P + rbase_s + pl;
                     drow = (static_cast<long long>(b) * p.F + p.fb[me] + fl) * np_s + pl;
                 } else {
                     srow = (static_cast<long long>(b) * p.F + p.fb[s] + fl) * np_me + pl;
-                    drow = (static_cast<long long>(b) * nf_s + fl) * p.P + p.pb[me] + pl;
+                    drow = (static_cast<long long>(b) * nf_s + fl) * p.P + rbase_d + pl;
                 }
                 val[u] = __ldg(reinterpret_cast<const uint4*>(src + srow * p.ld_src + vc * 8));
                 doff[u] = drow * p.ld_dst + vc * 8;
@@ -109,6 +129,7 @@ int shard_exchange(const XchgParams& p, int num_sms, cudaStream_t stream) {
         max_np = max(max_np, p.pb[r + 1] - p.pb[r]);
     }
     const long long vecs = static_cast<long long>(p.B) * max_nf * max_np * (p.C >> 3);
+    if (vecs >= (1LL << 31)) return -1;      // the copy loop indexes 16-byte vectors with 32 bits
     long long nblk = (vecs + 4 * kXThreads - 1) / (4 * kXThreads);
     const long long cap = (2LL * num_sms + nr - 1) / nr;
     if (nblk > cap) nblk = cap;
