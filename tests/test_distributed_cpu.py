@@ -178,3 +178,29 @@ def test_cfg_split_times_frame_shard_groups_world4():
         assert tsum == 4 * pair + 1 and usum == (2.0 if role == 0 else 4.0)
         assert (rg_rank, rg_ws) == (rank // 2, 2)
         assert (ec, eu) == (2.0 * pair, 2.0 * pair + 1)
+
+
+def test_exchange_kernel_magic_division_is_exact():
+    """csrc/shard.cu indexes 16-byte vectors with 32-bit round-up magic numbers (Granlund-Montgomery) instead of integer divisions:
+    q = (t + ((n - t) >> s1)) >> s2, t = umulhi(m, n), m = floor(2^32 (2^l - d) / d) + 1, l = ceil(log2 d).  The same arithmetic in
+    Python must equal n // d for every 32-bit n, for the divisors the kernel uses (channels / 8, pixels and frames of a block)."""
+    import random
+
+    def magic(d):
+        l = 0
+        while (1 << l) < d:
+            l += 1
+        m = (((1 << 32) * ((1 << l) - d)) // d + 1) & 0xffffffff
+        s1 = min(l, 1)
+        return m, s1, l - s1
+
+    def fdiv(n, mg):
+        m, s1, s2 = mg
+        t = (m * n) >> 32
+        return ((t + (((n - t) & 0xffffffff) >> s1)) & 0xffffffff) >> s2
+    rng = random.Random(3)
+    divisors = [1, 2, 3, 5, 7, 8, 15, 16, 40, 63, 80, 125, 128, 160, 512, 1024, 9216] + [rng.randrange(1, 1 << 20) for _ in range(200)]
+    for d in divisors:
+        mg = magic(d)
+        for n in [0, 1, d - 1, d, d + 1, 2 * d - 1, (1 << 31) - 1, (1 << 32) - 1] + [rng.randrange(0, 1 << 32) for _ in range(100)]:
+            assert fdiv(n, mg) == n // d, (n, d)
