@@ -35,6 +35,9 @@ namespace {
 #ifndef T2V_RES_LATE
 #define T2V_RES_LATE 1
 #endif
+#ifndef T2V_RES_DEPTH
+#define T2V_RES_DEPTH 3
+#endif
 #ifndef T2V_EPI_PIPE
 #define T2V_EPI_PIPE 0
 #endif
@@ -453,8 +456,15 @@ __global__ void __launch_bounds__(n_threads(GEGLU), 1) gemm_tc_kernel(const __gr
             const int ocol0 = geglu ? tn * (BN / 2) : tn * BN;
             const __half* res_row = (g.residual != nullptr && valid) ? g.residual + grow * g.ldr + ocol0 : nullptr;
 
-            uint4 rnext[NV];
-            auto prefetch_res = [&](int ci) {
+            // Residual row segments are fetched kResDepth chunks ahead into a register queue (static indices only).  The timeline
+            // (profiles/r02_gemm_timeline.md) showed ~1000 clk of exposed fetch latency per chunk with one chunk of look-ahead issued
+            // after the previous chunk's store; with depth 3 a 160-wide tile (3 + 2 chunks per warp pair) has its whole residual in
+            // flight while the warp still waits for the accumulator, and no generic load is outstanding at the chunk's fence.
+            // (wider tiles keep depth 1: their epilogue has no registers to spare -- 224 / 256 spilled and the residual-free layers
+            //  lost 5-12 % with the queue compiled in; A/B in profiles/r02_gemm_residual_depth_ab.txt: out-projection 34.8 -> 31.3 us)
+            constexpr int kResDepth = (GEGLU || BN > 160) ? 1 : T2V_RES_DEPTH;
+            uint4 rq[kResDepth][NV];
+            auto load_res = [&](uint4 (&dst)[NV], int ci) {
                 if (res_row != nullptr && vec_ok) {
                     if (vec32) {
 #pragma unroll
@@ -462,20 +472,24 @@ __global__ void __launch_bounds__(n_threads(GEGLU), 1) gemm_tc_kernel(const __gr
                             const int col = ci * CW + k * 8;
                             if (ocol0 + col < nvalid) {
                                 const U32x8 t8 = ldg_256(res_row + col);
-                                rnext[k] = make_uint4(t8.v[0], t8.v[1], t8.v[2], t8.v[3]);
-                                rnext[k + 1] = make_uint4(t8.v[4], t8.v[5], t8.v[6], t8.v[7]);
+                                dst[k] = make_uint4(t8.v[0], t8.v[1], t8.v[2], t8.v[3]);
+                                dst[k + 1] = make_uint4(t8.v[4], t8.v[5], t8.v[6], t8.v[7]);
                             }
                         }
                     } else {
 #pragma unroll
                         for (int k = 0; k < NV; ++k) {
                             const int col = ci * CW + k * 8;
-                            if (ocol0 + col < nvalid) rnext[k] = __ldg(reinterpret_cast<const uint4*>(res_row + col));
+                            if (ocol0 + col < nvalid) dst[k] = __ldg(reinterpret_cast<const uint4*>(res_row + col));
                         }
                     }
                 }
             };
-            if constexpr (!GEGLU) { if (hsel < nchunks) prefetch_res(hsel); }
+            if constexpr (!GEGLU) {
+#pragma unroll
+                for (int d = 0; d < kResDepth; ++d)
+                    if (hsel + d * CSTEP < nchunks) load_res(rq[d], hsel + d * CSTEP);
+            }
             float bstage = 0.f, cstage = 0.f;
             if (bias_staged && et < BN) {
                 const int col = tn * BN + et;
@@ -578,13 +592,17 @@ __global__ void __launch_bounds__(n_threads(GEGLU), 1) gemm_tc_kernel(const __gr
                 } else {
                 uint4 rcur[NV];
 #pragma unroll
-                for (int k = 0; k < NV; ++k) rcur[k] = rnext[k];
+                for (int k = 0; k < NV; ++k) rcur[k] = rq[0][k];
+#pragma unroll
+                for (int d = 0; d + 1 < kResDepth; ++d)
+#pragma unroll
+                    for (int k = 0; k < NV; ++k) rq[d][k] = rq[d + 1][k];
                 // ncu (profiles/r02_ncu_gemm_k320.md): fence.proxy.async in the TMA-store path waits for EVERY outstanding generic
                 // memory operation of the thread, so a residual prefetch issued here is paid in full at the fence of this very
                 // chunk (long-scoreboard stall on FENCE.VIEW.ASYNC).  On that path the prefetch of the next chunk is issued
                 // after this chunk's store instead (T2V_RES_LATE); it then overlaps the next chunk's TMEM load.
                 constexpr bool kResLate = T2V_RES_LATE != 0;
-                if (!(kResLate && tma_st) && ci + CSTEP < nchunks) prefetch_res(ci + CSTEP);
+                if (!(kResLate && tma_st) && ci + kResDepth * CSTEP < nchunks) load_res(rq[kResDepth - 1], ci + kResDepth * CSTEP);
                 const int pcol = tn * BN + c0;                    // packed (accumulator) column of v[0]
                 float bv[CW];
                 if (bias_staged) {
@@ -664,7 +682,7 @@ __global__ void __launch_bounds__(n_threads(GEGLU), 1) gemm_tc_kernel(const __gr
                         }
                         bulk_commit();
                     }
-                    if (kResLate && ci + CSTEP < nchunks) prefetch_res(ci + CSTEP);
+                    if (kResLate && ci + kResDepth * CSTEP < nchunks) load_res(rq[kResDepth - 1], ci + kResDepth * CSTEP);
                 } else
                 if (valid && !(g.flags & GEMM_DBG_NO_STORE)) {
                     if (res_row != nullptr) {
