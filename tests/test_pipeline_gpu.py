@@ -66,6 +66,50 @@ def test_short_trajectory_and_decode_vs_oracle(pipe):
     assert np.abs(got.astype(int) - ref_u8.astype(int)).mean() < 3.0
 
 
+@pytest.mark.parametrize('sampler', ['DDIM_Gaussian', 'DDIM'])
+def test_eta_positive_matches_oracle_on_the_same_noise(pipe, sampler, monkeypatch):
+    """eta > 0: the fused step kernel's sigma / direction terms against the oracle (gaussian_sampler.py:269-283, ddim/sampler.py:
+    199-218).  The GPU path draws its per-step noise from the CUDA generator and the oracle from the CPU one, so both sides are fed
+    the SAME noise tape here: the product through its single noise hook (`distributed.step_noise`), the oracle through torch.randn /
+    randn_like.  DDIM_Gaussian's reference draws a second, unused randn per step (the inpaint hook, :285-291): the tape skips it."""
+    p, cfg, W, Wv = pipe
+    c, uc = conds()
+    S, F, eta = 4, 2, 0.7
+    tape = [torch.randn((1, 4, F, 8, 8), generator=torch.Generator('cpu').manual_seed(500 + i)) for i in range(S)]
+    from t2v_b200 import distributed as D
+    it = iter(tape)
+    monkeypatch.setattr(D, 'step_noise', lambda like: next(it).to(device=like.device, dtype=like.dtype))
+    _, latent, _ = p.infer(c, uc, S, F, 77, 5.0, 64, 64, eta, 'GPU (half precision)', torch.device('cuda'), None, 0,
+                           0.0, None, False, sampler)
+    monkeypatch.undo()
+    Wh = {k: v.half().float() for k, v in W.items()}
+    x_T = torch.randn((1, 4, F, 8, 8), generator=torch.Generator('cpu').manual_seed(77))
+    calls = {'n': 0}
+    real_randn, real_randn_like = torch.randn, torch.randn_like
+
+    def tape_randn_like(x, *a, **k):                      # DDIM_Gaussian: draw 0, 2, 4, ... are the step noises
+        i = calls['n']
+        calls['n'] += 1
+        return tape[i // 2].to(x) if i % 2 == 0 else real_randn_like(x, *a, **k)
+
+    def tape_randn(*a, **k):                              # DDIM: one draw per step
+        i = calls['n']
+        calls['n'] += 1
+        return tape[i]
+    model = lambda a, b, d: UO.unet_forward(Wh, cfg, a, b, d)     # noqa: E731
+    if sampler == 'DDIM_Gaussian':
+        monkeypatch.setattr(torch, 'randn_like', tape_randn_like)
+        ref = SO.ddim_gaussian_sample(model, SO.linear_sd_betas(), x_T, S, c.float(), uc.float(), 5.0, eta=eta)
+    else:
+        monkeypatch.setattr(torch, 'randn', tape_randn)
+        ref = SO.ddim_sample(model, SO.linear_sd_betas(), x_T, S, c.float(), uc.float(), 5.0, eta=eta)
+    monkeypatch.undo()
+    assert calls['n'] == (2 * S if sampler == 'DDIM_Gaussian' else S)
+    err = float((latent.cpu() - ref).abs().max() / ref.abs().max())
+    report(f'pipeline:{sampler}_eta{eta}_4steps_tiny', max=err)
+    assert err < 6e-3, err                      # same budget as the eta = 0 trajectory (4 steps x 2 fp16 forwards vs fp32 oracle)
+
+
 def test_callback_and_interrupt(pipe):
     from t2v_b200 import samplers
     p = pipe[0]
