@@ -204,3 +204,40 @@ def test_exchange_kernel_magic_division_is_exact():
         mg = magic(d)
         for n in [0, 1, d - 1, d, d + 1, 2 * d - 1, (1 << 31) - 1, (1 << 32) - 1] + [rng.randrange(0, 1 << 32) for _ in range(100)]:
             assert fdiv(n, mg) == n // d, (n, d)
+
+
+def test_exchange_kernel_row_algebra_emulated():
+    """csrc/shard.cu moves the (own frames x peer's pixels) block of every rank with the row formulas
+         FS -> PS:  src row (b * nf_me + fl) * P + pb[s] + pl          -> dst row on rank s: (b * F + fb[me] + fl) * np_s + pl
+         PS -> FS:  src row (b * F + fb[s] + fl) * np_me + pl          -> dst row on rank s: (b * nf_s + fl) * P + pb[me] + pl
+    Emulated here in numpy for ragged frame / pixel partitions: FS -> PS must give every rank all F frames of its pixel range,
+    PS -> FS must be its inverse.  (The same formulas, with the same partition function, as the kernel -- this pins the algebra
+    on the CPU; the kernel itself is checked on GPUs by tests/test_frame_shard_gpu.py.)"""
+    import numpy as np
+    from t2v_b200.distributed import frame_bounds
+    for (B, F, P, nr) in [(2, 9, 12, 2), (1, 7, 10, 3), (2, 13, 8, 8), (1, 125, 16, 8)]:
+        fb, pb = frame_bounds(F, nr), frame_bounds(P, nr)           # the kernel partitions pixels with the same function
+        full = np.arange(B * F * P, dtype=np.int64).reshape(B, F, P)         # token id = (b, f, p)
+        fs = [full[:, fb[r]:fb[r + 1], :].reshape(-1).copy() for r in range(nr)]          # rows (b, own f, all p)
+        ps = [np.full(B * F * (pb[r + 1] - pb[r]), -1, dtype=np.int64) for r in range(nr)]
+        for me in range(nr):
+            nf_me = fb[me + 1] - fb[me]
+            for s in range(nr):
+                np_s = pb[s + 1] - pb[s]
+                for b in range(B):
+                    for fl in range(nf_me):
+                        for pl in range(np_s):
+                            ps[s][(b * F + fb[me] + fl) * np_s + pl] = fs[me][(b * nf_me + fl) * P + pb[s] + pl]
+        for r in range(nr):
+            assert np.array_equal(ps[r], full[:, :, pb[r]:pb[r + 1]].reshape(-1)), (B, F, P, nr, r)
+        back = [np.full(B * (fb[r + 1] - fb[r]) * P, -1, dtype=np.int64) for r in range(nr)]
+        for me in range(nr):
+            np_me = pb[me + 1] - pb[me]
+            for s in range(nr):
+                nf_s = fb[s + 1] - fb[s]
+                for b in range(B):
+                    for fl in range(nf_s):
+                        for pl in range(np_me):
+                            back[s][(b * nf_s + fl) * P + pb[me] + pl] = ps[me][(b * F + fb[s] + fl) * np_me + pl]
+        for r in range(nr):
+            assert np.array_equal(back[r], fs[r]), (B, F, P, nr, r)
