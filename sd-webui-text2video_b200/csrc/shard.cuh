@@ -84,8 +84,14 @@ __device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+// Bounded: a peer that never arrives (a rank died, or the ranks issued different launch sequences) must surface as a trapped
+// kernel -> a CUDA error in this process, never as a GPU spinning forever.  2^29 polls of >= 64 ns each are more than half a
+// minute, far beyond any legitimate skew between the ranks' graphs (plan construction happens before the first launch).
 __device__ __forceinline__ void spin_until_ge(const unsigned int* p, unsigned int e) {
-    while (static_cast<int>(ld_acquire_sys(p) - e) < 0) __nanosleep(64);
+    for (unsigned int spins = 0; static_cast<int>(ld_acquire_sys(p) - e) < 0; ++spins) {
+        __nanosleep(64);
+        if (spins > (1u << 29)) __trap();
+    }
 }
 #endif
 
