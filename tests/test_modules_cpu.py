@@ -178,3 +178,65 @@ def test_inpainting_weight_schedule_matches_reference(frames, i_frames, spec):
             assert any(ch.isdigit() for ch in spec)
             return
         assert np.allclose(got, np.asarray(ref, dtype=np.float64), rtol=0, atol=1e-12)
+
+
+def test_stable_lora_processor_walk_and_flags_on_cpu():
+    """Host side of the LoRA hot-merge (stable_lora/stable_utils/lora_processor.py:202-246): which `<name>.lora_A/B` pairs reach
+    the device-side merge, with which flags -- on a CPU mirror whose `lora_merge` / `lora_clear` are replaced by recorders."""
+    from t2v_b200.modules import UNetSD
+    from t2v_b200.lora import StableLoraProcessor
+    with torch.device('meta'):
+        net = UNetSD(dim=64)
+    calls = []
+    net.lora_merge = lambda name, A, B, alpha, temporal_mean=False: calls.append((name, tuple(A.shape), tuple(B.shape), alpha, temporal_mean))
+    cleared = []
+    net.lora_clear = lambda: cleared.append(True)
+    r = 4
+    lin, conv2, conv3, proj = ('input_blocks.1.1.transformer_blocks.0.attn1.to_q', 'input_blocks.1.0.in_layers.2',
+                               'input_blocks.1.0.temopral_conv.conv1.2', 'input_blocks.1.1.proj_in')
+    lora = {lin + '.lora_A': torch.zeros(r, 64), lin + '.lora_B': torch.zeros(64, r),
+            conv2 + '.lora_A': torch.zeros(r, 64 * 9), conv2 + '.lora_B': torch.zeros(64, r),
+            conv3 + '.lora_A': torch.zeros(r, 64 * 9), conv3 + '.lora_B': torch.zeros(64, r),
+            proj + '.lora_A': torch.zeros(r, 64, 1), proj + '.lora_B': torch.zeros(64, r, 1),       # Conv1d-style tensors get squeezed (:222-223)
+            'not.a.module.lora_A': torch.zeros(r, 8), 'not.a.module.lora_B': torch.zeros(8, r)}
+    p = StableLoraProcessor()
+    assert p.process_lora(net, [lora], lora_alpha=0.5) == 4
+    got = {c[0]: c for c in calls}
+    assert got[lin + '.weight'][3:] == (0.5, False) and got[conv2 + '.weight'][4] is False
+    assert got[conv3 + '.weight'][4] is True                                   # Conv3d (3,1,1): product averaged over the kernel axis
+    assert got[proj + '.weight'][1] == (r, 64) and got[proj + '.weight'][2] == (64, r)
+    calls.clear()
+    assert p.process_lora(net, [lora], use_conv=False) == 2 and {c[0] for c in calls} == {lin + '.weight', proj + '.weight'}
+    calls.clear()
+    assert p.process_lora(net, [lora], use_time=False) == 3 and conv3 + '.weight' not in {c[0] for c in calls}
+    assert p.process_lora(net, [], undo_merge=True) == 0 and cleared == [True] and p.previous is None
+    with pytest.raises(NotImplementedError):
+        p.process_lora(net, [lora], use_bias=True)
+    with pytest.raises(TypeError):
+        p.process_lora(nn.Linear(2, 2), [lora])
+
+
+def test_default_video_encoder_returns_a_data_url_with_exact_frames():
+    """process_modelscope returns data-URL strings like the reference (process_modelscope.py:34).  Without ffmpeg the default
+    encoder wraps the frames in an uncompressed RIFF AVI: decode the URL again and compare the pixels."""
+    import base64
+    import struct
+    import numpy as np
+    from t2v_b200 import video_encode as VE
+    rng = np.random.default_rng(0)
+    frames = [rng.integers(0, 256, size=(6, 5, 3), dtype=np.uint8) for _ in range(3)]       # odd width: rows are padded to 4 bytes
+    raw = VE._avi_bytes(frames, 8.0)
+    assert raw[:4] == b'RIFF' and raw[8:12] == b'AVI ' and struct.unpack('<I', raw[4:8])[0] == len(raw) - 8
+    url = VE.default_video_encoder(frames)
+    assert url.startswith('data:video/mp4;base64,') or url.startswith('data:video/avi;base64,')
+    if url.startswith('data:video/avi'):
+        assert base64.b64decode(url.split(',', 1)[1]) == VE._avi_bytes(frames, 15.0)
+    # frame payloads: '00db' chunks, bottom-up rows of w*3 bytes padded to a multiple of 4
+    pos, got = raw.index(b'movi') + 4, []
+    for _ in frames:
+        assert raw[pos:pos + 4] == b'00db'
+        n = struct.unpack('<I', raw[pos + 4:pos + 8])[0]
+        rows = np.frombuffer(raw[pos + 8:pos + 8 + n], dtype=np.uint8).reshape(6, 16)[:, :15].reshape(6, 5, 3)
+        got.append(rows[::-1])
+        pos += 8 + n + (n & 1)
+    assert all(np.array_equal(a, b) for a, b in zip(got, frames))
