@@ -87,3 +87,42 @@ def test_prompt_chunks_weights_and_padding():
     zw = e.process_tokens([c0.tokens, chunks[0].tokens], w).float().cpu()
     refw = CO.process_tokens(CO.clip_text_forward(Wh, cfg, torch.cat([toks, torch.tensor([chunks[0].tokens])])), w)
     assert ((zw - refw).pow(2).mean().sqrt() / refw.pow(2).mean().sqrt()).item() < 3e-3
+
+
+def test_prompt_chunking_host_logic_on_cpu(monkeypatch):
+    """Pure host logic of FrozenOpenCLIPEmbedder (clip_hardcode.py:146-260, :395-420): 75-token chunks framed by start / end ids,
+    BREAK starts a new chunk, padding after the first end token, emphasis multipliers with mean restoration -- checked without a
+    GPU by standing the CPU oracle in for the transformer (only here, as the checker)."""
+    from t2v_b200.clip import FrozenOpenCLIPEmbedder
+    cfg = CO.ClipConfig(width=128, heads=2, layers=4, layers_run=3, context=77, vocab=300)
+    with torch.device('meta'):
+        e = FrozenOpenCLIPEmbedder(width=cfg.width, heads=cfg.heads, layers=cfg.layers, vocab=cfg.vocab, tokenizer=FakeTokenizer())
+    W = UO.make_weights(CO.clip_param_specs(cfg), seed=4)
+    seen = {}
+
+    def fake_transformer(tokens):
+        seen['tokens'] = tokens.clone()
+        return CO.clip_text_forward(W, cfg, tokens)
+    monkeypatch.setattr(e, 'encode_with_transformer', fake_transformer)
+    long = ' '.join(f'word{i}' for i in range(160))                      # 160 tokens -> 75 + 75 + 10
+    chunks, count = e.tokenize_line(long)
+    assert count == 160 and len(chunks) == 3 and all(len(c.tokens) == 77 and len(c.multipliers) == 77 for c in chunks)
+    assert all(c.tokens[0] == e.id_start and c.tokens[-1] == e.id_end for c in chunks)
+    assert chunks[2].tokens[11:] == [e.id_end] * 66 and e.get_target_prompt_token_count(count) == 225
+    assert e.get_target_prompt_token_count(0) == 75 and len(e.empty_chunk().tokens) == 77
+    monkeypatch.setattr(e, '_parse', lambda line: [['a b', 1.0], ['BREAK', -1], ['c', 1.4]])
+    chunks, count = e.tokenize_line('ignored')
+    assert len(chunks) == 2 and count == 3 and chunks[1].multipliers[1] == 1.4 and chunks[1].multipliers[2] == 1.0
+    monkeypatch.undo()
+    monkeypatch.setattr(e, 'encode_with_transformer', fake_transformer)
+    z = e.encode(['a cat', long])                                         # batch of prompts with 1 and 3 chunks
+    assert z.shape == (2, 3 * 77, 128)
+    assert seen['tokens'].shape == (2, 77) and int(seen['tokens'][0, 2:].abs().sum()) == 0      # third chunk of 'a cat': empty chunk, padded
+    c0 = e.tokenize_line('a cat')[0][0]
+    toks = torch.tensor([c0.tokens])
+    toks[0, c0.tokens.index(e.id_end) + 1:] = e.id_pad
+    w = [[1.0] * 2 + [1.5] * 3 + [1.0] * 72]
+    got = e.process_tokens([c0.tokens], w)
+    assert torch.equal(seen['tokens'], toks)
+    ref = CO.process_tokens(CO.clip_text_forward(W, cfg, toks), w)
+    assert torch.allclose(got, ref, rtol=0, atol=1e-6)
